@@ -1,0 +1,124 @@
+/* tvb.h — C ABI of the B200-native token-Voicebox mel generator (libtvb.so).
+ *
+ * Drop-in boundary for ONE path of ishine/usdm: the flow-matching ODE sampler of src/decoder
+ * (reference files: src/decoder/voicebox/model/voicebox.py, src/decoder/voicebox/model/networks.py).
+ * Plain pointers and sizes only; no torch / C++ types cross this boundary.  Every function returns
+ * 0 on success or a negative tvb_status; tvb_last_error() gives a human-readable message for the
+ * calling thread's most recent failure.  No exception crosses the ABI.
+ *
+ * Conventions
+ *  - "dev" pointers are CUDA device pointers on the handle's device; "host" pointers are ordinary memory.
+ *  - `stream` is a cudaStream_t passed as void* (torch: torch.cuda.current_stream().cuda_stream).  All work is
+ *    enqueued on it; no call synchronises the device except tvb_load_weight/tvb_finalize_weights/tvb_destroy.
+ *  - A handle is not thread-safe.  It owns its packed weights and an internal workspace; inputs are borrowed
+ *    for the duration of the enqueued work and never written.
+ *  - Tensor layouts are the reference's: x int64 [B,T]; y/z/cond/noise/out fp32 [B,n_feats,T] contiguous.
+ *  - Padded frames (tau >= lengths[b]) of every output are exactly 0, as in the reference (networks.py:372).
+ */
+#ifndef TVB_H_
+#define TVB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tvb_handle tvb_handle;
+
+typedef enum tvb_status {
+    TVB_OK = 0,
+    TVB_ERR_INVALID = -1,     /* bad argument / unsupported configuration (Python wrapper raises ValueError) */
+    TVB_ERR_CUDA = -2,        /* CUDA runtime / driver failure            (RuntimeError) */
+    TVB_ERR_STATE = -3,       /* call order violated, e.g. weights not finalized (RuntimeError) */
+    TVB_ERR_NOMEM = -4
+} tvb_status;
+
+typedef enum tvb_precision {
+    TVB_PRECISION_BF16 = 0,           /* tcgen05 bf16 tensor-core path, fp32 accumulate / residual / softmax / LN */
+    TVB_PRECISION_FP32_VALIDATE = 1   /* all-fp32 CUDA-core path used to validate against the fp32 reference   */
+} tvb_precision;
+
+typedef enum tvb_solver { TVB_SOLVER_EULER = 0, TVB_SOLVER_HEUN = 1 } tvb_solver;
+
+/* Mirrors the keyword arguments of reference Voicebox.__init__ (voicebox.py:154-156) that shape the network. */
+typedef struct tvb_config {
+    int32_t n_feats;              /* 80   */
+    int32_t n_tokens;             /* 10000 (the estimator embeds n_tokens + 1 ids; id n_tokens = unconditional) */
+    int32_t embedding_dim;        /* 1280 */
+    int32_t hidden_size;          /* 1024 */
+    int32_t intermediate_size;    /* 4096 */
+    int32_t num_attention_heads;  /* 16   */
+    int32_t num_hidden_layers;    /* 24   */
+    int32_t convpos_width;        /* 31   */
+    int32_t convpos_groups;       /* 16   */
+    int32_t convpos_depth;        /* 2    */
+    float sigma_min;              /* 1e-4 */
+} tvb_config;
+
+/* Replaces: Voicebox.__init__ (voicebox.py:153-176) -> Transformer.__init__ (networks.py:270-300). */
+int tvb_create(const tvb_config* cfg, int device, tvb_handle** out);
+int tvb_destroy(tvb_handle* h);
+
+/* Replaces: nn.Module.load_state_dict / PyTorchModelHubMixin.from_pretrained (voicebox.py:10,153).
+ * `ref_key` is the reference state-dict key (e.g. "estimator.layers.3.attention.q_proj.weight",
+ * "estimator.pos_conv_embeds.0.conv.parametrizations.weight.original1"); data is fp32, contiguous, host or device. */
+int tvb_load_weight(tvb_handle* h, const char* ref_key, const void* data, const int64_t* shape, int32_t ndim);
+/* Folds weight-norm and the q scaling, builds the unit-embedding->hidden gather table, packs bf16 copies. */
+int tvb_finalize_weights(tvb_handle* h);
+
+int tvb_set_precision(tvb_handle* h, int32_t precision);
+int tvb_get_precision(const tvb_handle* h);
+/* Ablation / cross-check switches of the bf16 path: "attn_tc" and "conv_tc" (1 = tcgen05 kernel, default;
+ * 0 = the CUDA-core kernel of the same op).  Both are GPU kernels of this library; there is no CPU path. */
+int tvb_set_option(tvb_handle* h, const char* name, int32_t value);
+
+/* Replaces: Transformer.forward(x, y, cond, t, lengths) (networks.py:302-374) — the per-step velocity estimator.
+ * x_dev int64 [B,T]; y_dev, cond_dev fp32 [B,n_feats,T]; t_host fp32 [B]; lengths_host int64 [B];
+ * out_v_dev fp32 [B,n_feats,T]. */
+int tvb_estimator_forward(tvb_handle* h, const int64_t* x_dev, const float* y_dev, const float* cond_dev,
+                          const float* t_host, const int64_t* lengths_host, int32_t B, int32_t T,
+                          float* out_v_dev, void* stream);
+
+/* Replaces: CFM.sample (voicebox.py:51-72): classifier-free-guidance doubling [uncond ; cond] in one pass and
+ * the combine v_c + g (v_c - v_u).  t is uniform over the batch (as in the reference).  gradient_scale <= 0
+ * runs the conditional branch only; speech_prompt == 0 zeroes cond (voicebox.py:56-58). */
+int tvb_sample_cfg(tvb_handle* h, const int64_t* x_dev, const float* z_dev, const float* cond_dev,
+                   const int64_t* lengths_host, int32_t B, int32_t T, float t, float gradient_scale,
+                   int32_t speech_prompt, float* out_v_dev, void* stream);
+
+/* Replaces: CFM.solve_euler / CFM.solve_heun (voicebox.py:74-138), i.e. the whole ODE loop of CFM.generate.
+ *  t_span_host      fp32 [n_steps + 1]  (generate(): linspace(0, 1, n + 1), voicebox.py:145)
+ *  z0_dev           fp32 [B,n_feats,T]  initial noise (generate(): randn_like(cond), voicebox.py:142)
+ *  prompt_noise_dev fp32 [n_noise,B,n_feats,T] or NULL: the fresh randn_like(cond) draws the reference makes after
+ *                   each (sub)step when speech_prompt (voicebox.py:90,116,127), in call order;
+ *                   n_noise = n_steps (Euler) or 2*n_steps-1 (Heun).  Required iff speech_prompt && prompt_len > 0.
+ *  prompt_len       prompt_lengths[0] of the reference (batch-uniform, voicebox.py:92)
+ *  out_mel_dev      fp32 [B,n_feats,T]  (the reference returns the full length, prompt region included)
+ *  step_v_dev       optional fp32 [n_evals,B,n_feats,T]: guided velocity of every estimator evaluation
+ *                   (parity hook for the per-step velocity test), or NULL. */
+int tvb_solve(tvb_handle* h, int32_t solver, const int64_t* x_dev, const float* z0_dev, const float* cond_dev,
+              const int64_t* lengths_host, int32_t B, int32_t T, int32_t prompt_len, int32_t n_steps,
+              const float* t_span_host, float gradient_scale, int32_t speech_prompt,
+              const float* prompt_noise_dev, float* out_mel_dev, float* step_v_dev, void* stream);
+
+/* Number of this library's kernels launched by the handle since creation (bench.py's gpu_launches). */
+int64_t tvb_kernel_launches(const tvb_handle* h);
+/* Bytes of device memory currently held by the handle (weights + workspace). */
+int64_t tvb_device_bytes(const tvb_handle* h);
+
+/* Kernel-level test hooks (used by tests/ only): a single tcgen05 GEMM  C = A * W^T + bias with a chosen epilogue.
+ * a_dev bf16 [M,K], w_dev bf16 [N,K], bias_dev fp32 [N] or NULL, resid_dev fp32 [M,N] or NULL,
+ * out_f32_dev fp32 [M,N] or NULL, out_bf16_dev bf16 [M,N] or NULL.  epilogue: 0 bf16, 1 gelu->bf16, 2 +resid->f32,
+ * 3 f32+bf16, 4 f32.  M % 128 == 0, N % 256 == 0, K % 64 == 0. */
+int tvb_debug_gemm_bf16(int device, const void* a_dev, const void* w_dev, const float* bias_dev, const float* resid_dev,
+                        float* out_f32_dev, void* out_bf16_dev, int32_t M, int32_t N, int32_t K, int32_t epilogue,
+                        void* stream);
+
+const char* tvb_last_error(void);
+const char* tvb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVB_H_ */

@@ -1,0 +1,85 @@
+"""CPU: the C-ABI library loads, exports every symbol include/tvb.h declares, and fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from util import CFG, ROOT
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "tvb.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(tvb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from usdm_b200 import engine
+    lib = engine.load_library()
+    syms = _declared_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(lib, s), f"libtvb.so does not export {s}"
+        assert s in engine._SIGNATURES, f"{s} has no ctypes signature in usdm_b200/engine.py"
+    assert set(engine._SIGNATURES) == set(syms)
+    assert b"sm_100a" in lib.tvb_version()
+
+
+def test_only_sm100a_code_in_library():
+    import subprocess, shutil
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    from usdm_b200 import engine
+    out = subprocess.run([cuobjdump, "-lelf", engine.library_path()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_create_fails_loudly_without_gpu():
+    from usdm_b200 import engine
+    lib = engine.load_library()
+    cfg = engine.TvbConfig(80, 10000, 1280, 1024, 4096, 16, 24, 31, 16, 2, 1e-4)
+    h = C.c_void_p()
+    rc = lib.tvb_create(C.byref(cfg), 0, C.byref(h))
+    assert rc == engine.ERR_CUDA
+    assert b"no CPU path" in lib.tvb_last_error()
+    with pytest.raises(RuntimeError):
+        engine.check(rc)
+
+
+def test_create_rejects_unsupported_config():
+    from usdm_b200 import engine
+    lib = engine.load_library()
+    cfg = engine.TvbConfig(80, 10000, 1280, 1000, 4096, 16, 24, 31, 16, 2, 1e-4)   # head_dim != 64
+    h = C.c_void_p()
+    rc = lib.tvb_create(C.byref(cfg), 0, C.byref(h))
+    assert rc == engine.ERR_INVALID
+    with pytest.raises(ValueError):
+        engine.check(rc)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_voicebox_has_no_cpu_path():
+    import usdm_b200
+    small = dict(CFG, num_hidden_layers=2)
+    m = usdm_b200.Voicebox(**small)
+    x = torch.zeros(1, 8, dtype=torch.long)
+    y = torch.zeros(1, 80, 8)
+    with pytest.raises(RuntimeError):
+        m.estimator(x, y, y, torch.tensor([0.5]), torch.tensor([8]))
+    with pytest.raises(RuntimeError):
+        m.generate(x, y, torch.tensor([8]), 2)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "usdm_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} references the oracle"
+                assert "/root/reference" not in src

@@ -1,0 +1,204 @@
+// bf16 x bf16 -> fp32 GEMM on the 5th-gen tensor cores:  C[M,N] = A[M,K] * W[N,K]^T (+ fused epilogue)
+//
+// Replaces every nn.Linear on the hot path (reference networks.py:162-166 q/k/v, :208 out_proj, :226/:230 FFN,
+// :363 skip merge).  Both operands are K-major (nn.Linear weights are stored [out, in], activations [tokens, in]).
+//
+// Structure (one CTA per SM, persistent over output tiles):
+//   warp 0      : TMA producer   (cp.async.bulk.tensor 2D, SWIZZLE_128B boxes of 64 bf16 columns, 4-stage ring)
+//   warp 1      : MMA issuer     (one elected thread: tcgen05.mma.cta_group::1.kind::f16, M=128, N=256, K=16)
+//   warps 2..5  : epilogue       (tcgen05.ld 32x32b from TMEM, bias / GELU / residual, vectorised global stores)
+// TMEM holds two 128x256 fp32 accumulators (512 columns) so the epilogue of tile i overlaps the mainloop of tile i+1.
+#pragma once
+#include "common.cuh"
+
+namespace tvb {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BN = 256;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;                 // 16 KB
+constexpr int GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;                 // 32 KB
+constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;       // 48 KB
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GEMM_THREADS = 192;
+
+enum GemmEpilogue : int {
+    EPI_BF16 = 0,        // out_bf16 = acc + bias
+    EPI_GELU_BF16 = 1,   // out_bf16 = gelu_erf(acc + bias)
+    EPI_RESID_F32 = 2,   // out_f32  = acc + bias + resid
+    EPI_DUAL = 3,        // out_f32  = acc + bias ; out_bf16 = bf16(out_f32)
+    EPI_F32 = 4,         // out_f32  = acc + bias
+};
+
+struct GemmParams {
+    int M, N, K;          // M % 128 == 0, N % 256 == 0, K % 64 == 0
+    int K1;               // columns [0,K1) of the reduction come from A, [K1,K) from A2 (skip-merge concat); K1 == K if unused
+    const float* bias;    // [N] or nullptr
+    const float* resid;   // [M, ld_out] fp32 (EPI_RESID_F32)
+    float* out_f32;       // [M, ld_out]
+    __nv_bfloat16* out_bf16;
+    int ld_out;           // row stride of outputs / resid, in elements
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + GEMM_STAGES;
+    uint64_t* tfull_bar = empty_bar + GEMM_STAGES;     // [2] accumulator ready
+    uint64_t* tempty_bar = tfull_bar + 2;              // [2] accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tiles_n = p.N / GEMM_BN;
+    const int num_tiles = (p.M / GEMM_BM) * tiles_n;
+    const int num_kb = p.K / GEMM_BK;
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmA2);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp_idx == 1 && lane == 0) {
+        for (int s = 0; s < GEMM_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 4);   // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp_idx == 2) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp_idx == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * GEMM_BM;
+                const int n0 = (tile % tiles_n) * GEMM_BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * GEMM_STAGE_BYTES;
+                    uint8_t* sb = sa + GEMM_A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], GEMM_STAGE_BYTES);
+                    const int k0 = kb * GEMM_BK;
+                    if (k0 < p.K1) tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);
+                    else           tma_load_2d(sa, &tmA2, &full_bar[stage], k0 - p.K1, m0);
+                    tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+                    if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ------------------------------ MMA issuer ------------------------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, GEMM_BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * GEMM_BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * GEMM_STAGE_BYTES);
+                    const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+                    const uint64_t db = make_smem_desc_sw128(sa + GEMM_A_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        // advancing 16 bf16 (32 B) along K inside the 128-B swizzle atom = +2 in the (>>4) address field
+                        umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);          // smem slot reusable once these MMAs retire
+                    if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[as]);                 // accumulator complete
+            }
+        }
+    } else {
+        // ------------------------------ epilogue warps ------------------------------
+        const int quad = warp_idx & 3;                       // TMEM lane quadrant this warp may access
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const int m0 = (tile / tiles_n) * GEMM_BM;
+            const int n0 = (tile % tiles_n) * GEMM_BN;
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+            const int row = m0 + quad * 32 + lane;
+            const size_t row_off = static_cast<size_t>(row) * p.ld_out;
+#pragma unroll 1
+            for (int c = 0; c < GEMM_BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * GEMM_BN + c * 32, r);
+                tmem_ld_wait();
+                const int col = n0 + c * 32;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.bias != nullptr) {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = __ldg(b4 + j);
+                        v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                    }
+                }
+                if constexpr (EPI == EPI_GELU_BF16) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                }
+                if constexpr (EPI == EPI_RESID_F32) {
+                    const float4* r4 = reinterpret_cast<const float4*>(p.resid + row_off + col);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = r4[j];
+                        v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                    }
+                }
+                if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_DUAL || EPI == EPI_F32) {
+                    float4* o4 = reinterpret_cast<float4*>(p.out_f32 + row_off + col);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                if constexpr (EPI == EPI_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_DUAL) {
+                    uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + row_off + col);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 2) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace tvb

@@ -1,0 +1,858 @@
+// libtvb: C-ABI engine of the B200-native token-Voicebox mel generator (see include/tvb.h).
+// Host-side orchestration only lives here: weight packing, the packed row layout ("plan"), the per-step kernel
+// sequence and the ODE loop.  All arithmetic runs in the kernels of gemm_tc.cuh / attn_tc.cuh / conv_tc.cuh / simt.cuh.
+// There is deliberately no CPU implementation of anything: without a CUDA device every compute entry point fails.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/tvb.h"
+#include "attn_tc.cuh"
+#include "conv_tc.cuh"
+#include "gemm_tc.cuh"
+#include "simt.cuh"
+
+using namespace tvb;
+typedef __nv_bfloat16 bf16;
+
+// ----------------------------------------------------------------------------------------------------------------
+// error plumbing
+// ----------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess) return fail(TVB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+    } while (0)
+#define CKL() CK(cudaGetLastError())
+#define TRY(expr)                  \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != TVB_OK) return rc__; \
+    } while (0)
+
+// ----------------------------------------------------------------------------------------------------------------
+// TMA descriptor creation (driver entry point resolved at run time: no link-time dependency on libcuda)
+// ----------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled g_encode = nullptr;
+static int resolve_driver() {
+    if (g_encode) return TVB_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return fail(TVB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
+    return TVB_OK;
+}
+// 2-D bf16 row-major [rows, cols] (leading dimension ld elements), box = box_rows x 64 columns, 128-byte swizzle.
+static int make_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols = 64) {
+    TRY(resolve_driver());
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(TVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
+                                       (long long)rows, (long long)cols, (long long)ld);
+    return TVB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// handle
+// ----------------------------------------------------------------------------------------------------------------
+struct RawTensor {
+    float* p = nullptr;
+    std::vector<int64_t> shape;
+    size_t n = 0;
+};
+struct Lin {                 // one nn.Linear: y = x W^T + b
+    const float* w32 = nullptr;
+    bf16* w16 = nullptr;
+    const float* bias = nullptr;
+    int N = 0, K = 0;
+    CUtensorMap tm;          // B operand map: [N, K], box 256 x 64
+};
+struct Act {                 // an activation buffer [Mp, C] in the precision of the active path
+    float* f32 = nullptr;
+    bf16* b16 = nullptr;
+    int C = 0;
+    CUtensorMap tm;          // A operand map (bf16 path): box 128 x 64
+};
+struct LayerW {
+    Lin qkv, o, f1, f2;
+    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+};
+
+struct tvb_handle {
+    tvb_config cfg;
+    int device = 0;
+    int precision = TVB_PRECISION_BF16;
+    bool finalized = false;
+    int num_sms = 148;
+    int64_t launches = 0;
+    size_t dev_bytes = 0;       // weights
+    size_t ws_bytes = 0;        // workspace
+    int opt_attn_tc = 1;        // bf16 path: 1 = tcgen05 attention, 0 = CUDA-core attention (ablation / cross-check)
+    int opt_conv_tc = 1;        // bf16 path: 1 = tcgen05 positional conv, 0 = CUDA-core conv
+    std::vector<void*> owned;                    // weight-side allocations
+    std::map<std::string, RawTensor> raw;
+
+    // packed weights
+    float *G = nullptr, *b_in = nullptr, *Wy_t = nullptr, *Wc_t = nullptr, *freqs = nullptr, *slopes = nullptr;
+    std::vector<float*> conv_wp32;
+    std::vector<bf16*> conv_wp16;
+    std::vector<const float*> conv_bias;
+    std::vector<CUtensorMap> conv_tm;            // [G*taps*64, 64] bf16 packed weights, box 64 x 64
+    const float *ln0_g = nullptr, *ln0_b = nullptr;
+    std::vector<LayerW> layers;
+    std::vector<Lin> skip;
+    const float *w_out = nullptr, *b_out = nullptr;
+    bf16* w_out16 = nullptr;                     // [2][128 rows (n_feats padded), H] for the fused output kernel
+
+    // plan (row layout) + workspace
+    std::vector<void*> ws_owned;
+    int ws_cap_rows = 0, ws_precision = -1;
+    size_t ws_cap_state = 0;
+    RowLayout L{};
+    int *d_row_seq = nullptr, *d_row_pos = nullptr, *d_seq = nullptr;   // d_seq: 4 * nseq_cap ints
+    int seq_cap = 0;
+    int2* d_work16 = nullptr; int work16_cap = 0, n_work16 = 0;        // 16-query tiles (CUDA-core attention)
+    int4* d_work128 = nullptr; int work128_cap = 0, n_work128 = 0;     // 128-query tiles (tcgen05 attention)
+    float* d_tseq = nullptr;
+    int plan_B = 0, plan_T = 0, plan_cfg = 0, plan_half = 0;
+    float* base = nullptr;
+    Act hin, p1, slots[32], hbA, hbB, qkv, ctx, mid;
+    float *xpre = nullptr, *hres = nullptr, *vbuf = nullptr;
+    float *z_work = nullptr, *z_hat = nullptr, *v_pred = nullptr;
+    CUtensorMap tm_qkv_attn;                     // [Mp, 3H] box 128 x 64 (same as qkv.tm) kept for clarity
+};
+
+static int dev_alloc(tvb_handle* h, std::vector<void*>& bag, void** p, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) return fail(TVB_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    bag.push_back(*p);
+    if (&bag == &h->ws_owned) h->ws_bytes += bytes;
+    else h->dev_bytes += bytes;
+    return TVB_OK;
+}
+template <typename T>
+static int dev_alloc_t(tvb_handle* h, std::vector<void*>& bag, T** p, size_t n) {
+    return dev_alloc(h, bag, reinterpret_cast<void**>(p), n * sizeof(T));
+}
+
+static int grid_for(size_t n, int block = 256) {
+    size_t g = (n + block - 1) / block;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// create / destroy / weights
+// ----------------------------------------------------------------------------------------------------------------
+extern "C" const char* tvb_last_error(void) { return g_err.c_str(); }
+extern "C" const char* tvb_version(void) { return "tvb-b200 0.1 (sm_100a)"; }
+
+extern "C" int tvb_create(const tvb_config* cfg, int device, tvb_handle** out) {
+    if (!cfg || !out) return fail(TVB_ERR_INVALID, "null argument");
+    const tvb_config& c = *cfg;
+    if (c.hidden_size <= 0 || c.num_attention_heads <= 0 || c.hidden_size / c.num_attention_heads != 64 ||
+        c.hidden_size % c.num_attention_heads != 0)
+        return fail(TVB_ERR_INVALID, "unsupported: head_dim must be 64 (hidden %d, heads %d)", c.hidden_size, c.num_attention_heads);
+    if (c.hidden_size % 256 != 0 || c.hidden_size > 1024)
+        return fail(TVB_ERR_INVALID, "unsupported hidden_size %d (need multiple of 256, <= 1024)", c.hidden_size);
+    if (c.intermediate_size % 256 != 0) return fail(TVB_ERR_INVALID, "unsupported intermediate_size %d", c.intermediate_size);
+    if (c.embedding_dim % 16 != 0) return fail(TVB_ERR_INVALID, "unsupported embedding_dim %d", c.embedding_dim);
+    if (c.convpos_groups <= 0 || c.hidden_size / c.convpos_groups != 64 || c.hidden_size % c.convpos_groups != 0)
+        return fail(TVB_ERR_INVALID, "unsupported: conv channels per group must be 64");
+    if (c.convpos_width % 2 != 1 || c.convpos_width > 33) return fail(TVB_ERR_INVALID, "unsupported convpos_width %d (odd, <= 33)", c.convpos_width);
+    if (c.num_hidden_layers % 2 != 0 || c.num_hidden_layers > 64 || c.num_hidden_layers < 2)
+        return fail(TVB_ERR_INVALID, "unsupported num_hidden_layers %d", c.num_hidden_layers);
+    if (c.n_feats <= 0 || c.n_feats > 128 || c.n_feats % 16 != 0) return fail(TVB_ERR_INVALID, "unsupported n_feats %d", c.n_feats);
+    if (c.convpos_depth < 1 || c.convpos_depth > 2) return fail(TVB_ERR_INVALID, "unsupported convpos_depth %d (1 or 2)", c.convpos_depth);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(TVB_ERR_CUDA, "no CUDA device available (%s); libtvb has no CPU path", cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= ndev) return fail(TVB_ERR_INVALID, "device %d out of range", device);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(TVB_ERR_INVALID, "device %d is sm_%d%d; libtvb is built for sm_100a only", device, prop.major, prop.minor);
+    tvb_handle* h = new tvb_handle();
+    h->cfg = c;
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    *out = h;
+    return TVB_OK;
+}
+
+extern "C" int tvb_destroy(tvb_handle* h) {
+    if (!h) return TVB_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (void* p : h->owned) cudaFree(p);
+    for (void* p : h->ws_owned) cudaFree(p);
+    delete h;
+    return TVB_OK;
+}
+
+extern "C" int tvb_load_weight(tvb_handle* h, const char* key, const void* data, const int64_t* shape, int32_t ndim) {
+    if (!h || !key || !data || !shape || ndim < 1 || ndim > 4) return fail(TVB_ERR_INVALID, "bad argument to tvb_load_weight");
+    if (h->finalized) return fail(TVB_ERR_STATE, "weights already finalized");
+    CK(cudaSetDevice(h->device));
+    RawTensor t;
+    t.n = 1;
+    for (int i = 0; i < ndim; ++i) {
+        if (shape[i] <= 0) return fail(TVB_ERR_INVALID, "bad shape for %s", key);
+        t.shape.push_back(shape[i]);
+        t.n *= static_cast<size_t>(shape[i]);
+    }
+    auto it = h->raw.find(key);
+    if (it != h->raw.end()) {
+        if (it->second.n != t.n) return fail(TVB_ERR_INVALID, "weight %s reloaded with a different size", key);
+        t.p = it->second.p;
+    } else {
+        TRY(dev_alloc_t(h, h->owned, &t.p, t.n));
+    }
+    CK(cudaMemcpy(t.p, data, t.n * sizeof(float), cudaMemcpyDefault));
+    h->raw[key] = t;
+    return TVB_OK;
+}
+
+static int need(tvb_handle* h, const std::string& key, std::vector<int64_t> shape, const float** out) {
+    auto it = h->raw.find(key);
+    if (it == h->raw.end()) return fail(TVB_ERR_STATE, "missing weight %s", key.c_str());
+    if (it->second.shape != shape) {
+        std::string s;
+        for (auto d : it->second.shape) s += std::to_string(d) + ",";
+        return fail(TVB_ERR_INVALID, "weight %s has shape [%s], unexpected", key.c_str(), s.c_str());
+    }
+    *out = it->second.p;
+    return TVB_OK;
+}
+
+static int make_lin(tvb_handle* h, Lin* lin, const float* w32, const float* bias, int N, int K) {
+    lin->w32 = w32;
+    lin->bias = bias;
+    lin->N = N;
+    lin->K = K;
+    TRY(dev_alloc_t(h, h->owned, &lin->w16, static_cast<size_t>(N) * K));
+    k_f32_to_bf16<<<grid_for(static_cast<size_t>(N) * K), 256>>>(w32, lin->w16, static_cast<size_t>(N) * K);
+    CKL();
+    TRY(make_tmap(&lin->tm, lin->w16, N, K, K, GEMM_BN));
+    return TVB_OK;
+}
+
+template <int EPI>
+static int launch_sgemm(tvb_handle* h, const SgemmParams& p, cudaStream_t st) {
+    dim3 grid((p.N + 127) / 128, (p.M + 127) / 128);
+    k_sgemm<EPI><<<grid, 256, 0, st>>>(p);
+    h->launches++;
+    CKL();
+    return TVB_OK;
+}
+
+extern "C" int tvb_finalize_weights(tvb_handle* h) {
+    if (!h) return fail(TVB_ERR_INVALID, "null handle");
+    if (h->finalized) return TVB_OK;
+    CK(cudaSetDevice(h->device));
+    const tvb_config& c = h->cfg;
+    const int H = c.hidden_size, E = c.embedding_dim, F = c.intermediate_size, nf = c.n_feats, nl = c.num_hidden_layers;
+    const int taps = c.convpos_width, cpg = H / c.convpos_groups;
+    const std::string p = "estimator.";
+    const float *embed, *w_in, *b_in;
+    TRY(need(h, p + "embed.weight", {c.n_tokens + 1, E}, &embed));
+    TRY(need(h, p + "proj_in.weight", {H, 2 * nf + E, 1}, &w_in));
+    TRY(need(h, p + "proj_in.bias", {H}, &b_in));
+    h->b_in = const_cast<float*>(b_in);
+    const int ldin = 2 * nf + E;
+    // unit table: G[id] = sqrt(E) * embed[id] @ W_in[:, :E]^T                                  (networks.py:305-307)
+    TRY(dev_alloc_t(h, h->owned, &h->G, static_cast<size_t>(c.n_tokens + 1) * H));
+    {
+        SgemmParams sp{};
+        sp.M = c.n_tokens + 1; sp.N = H; sp.K = E; sp.K1 = E;
+        sp.A = embed; sp.lda = E; sp.A2 = embed; sp.lda2 = E;
+        sp.W = w_in; sp.ldw = ldin; sp.bias = nullptr; sp.resid = nullptr; sp.ldr = 0;
+        sp.C = h->G; sp.ldc = H; sp.alpha = sqrtf(static_cast<float>(E));
+        TRY(launch_sgemm<SG_PLAIN>(h, sp, 0));
+    }
+    TRY(dev_alloc_t(h, h->owned, &h->Wy_t, static_cast<size_t>(nf) * H));
+    TRY(dev_alloc_t(h, h->owned, &h->Wc_t, static_cast<size_t>(nf) * H));
+    k_transpose_slice<<<(nf * H + 255) / 256, 256>>>(w_in, ldin, E, nf, H, h->Wy_t);
+    k_transpose_slice<<<(nf * H + 255) / 256, 256>>>(w_in, ldin, E + nf, nf, H, h->Wc_t);
+    CKL();
+    // time-token frequencies f_k = exp(-k ln(1e4)/(H/2-1))                                    (networks.py:22-25)
+    {
+        std::vector<float> f(H / 2);
+        const double s = std::log(10000.0) / (H / 2 - 1);
+        const float sf = static_cast<float>(s);
+        for (int k = 0; k < H / 2; ++k) f[k] = static_cast<float>(std::exp(static_cast<double>(static_cast<float>(k) * -sf)));
+        TRY(dev_alloc_t(h, h->owned, &h->freqs, f.size()));
+        CK(cudaMemcpy(h->freqs, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice));
+        // ALiBi slopes (networks.py:99-115), heads = power of two or not
+        std::vector<float> sl;
+        auto pow2 = [](int n) {
+            std::vector<double> v;
+            const double start = std::pow(2.0, -std::pow(2.0, -(std::log2((double)n) - 3)));
+            for (int i = 0; i < n; ++i) v.push_back(start * std::pow(start, i));
+            return v;
+        };
+        const int nh = c.num_attention_heads;
+        const double l2 = std::log2((double)nh);
+        if (std::floor(l2) == l2) {
+            for (double v : pow2(nh)) sl.push_back(static_cast<float>(v));
+        } else {
+            const int cp = 1 << static_cast<int>(std::floor(l2));
+            for (double v : pow2(cp)) sl.push_back(static_cast<float>(v));
+            std::vector<double> ext = pow2(2 * cp);
+            for (int i = 0; i < nh - cp; ++i) sl.push_back(static_cast<float>(ext[2 * i]));
+        }
+        TRY(dev_alloc_t(h, h->owned, &h->slopes, sl.size()));
+        CK(cudaMemcpy(h->slopes, sl.data(), sl.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    // positional convs: fold weight norm, pack                                                (networks.py:67-95)
+    float* norms = nullptr;
+    TRY(dev_alloc_t(h, h->owned, &norms, 64));
+    for (int i = 0; i < c.convpos_depth; ++i) {
+        const std::string cp = p + "pos_conv_embeds." + std::to_string(i) + ".conv.";
+        const float *g, *v, *b;
+        TRY(need(h, cp + "parametrizations.weight.original0", {1, 1, taps}, &g));
+        TRY(need(h, cp + "parametrizations.weight.original1", {H, cpg, taps}, &v));
+        TRY(need(h, cp + "bias", {H}, &b));
+        float* w32; bf16* w16;
+        const size_t n = static_cast<size_t>(H) * cpg * taps;
+        TRY(dev_alloc_t(h, h->owned, &w32, n));
+        TRY(dev_alloc_t(h, h->owned, &w16, n));
+        k_conv_tap_norm<<<taps, 256>>>(v, H, cpg, taps, norms);
+        k_conv_pack<<<grid_for(n), 256>>>(v, g, norms, H, cpg, taps, w32, w16);
+        CKL();
+        CK(cudaDeviceSynchronize());
+        h->conv_wp32.push_back(w32);
+        h->conv_wp16.push_back(w16);
+        h->conv_bias.push_back(b);
+        CUtensorMap tm;
+        TRY(make_tmap(&tm, w16, static_cast<int64_t>(c.convpos_groups) * taps * cpg, cpg, cpg, 64));
+        h->conv_tm.push_back(tm);
+    }
+    TRY(need(h, p + "layer_norm.weight", {H}, &h->ln0_g));
+    TRY(need(h, p + "layer_norm.bias", {H}, &h->ln0_b));
+    // encoder layers
+    h->layers.resize(nl);
+    for (int l = 0; l < nl; ++l) {
+        const std::string lp = p + "layers." + std::to_string(l) + ".";
+        const float *wq, *wk, *wv, *bq, *bk, *bv, *wo, *bo, *w1, *b1, *w2, *b2;
+        TRY(need(h, lp + "attention.q_proj.weight", {H, H}, &wq));
+        TRY(need(h, lp + "attention.k_proj.weight", {H, H}, &wk));
+        TRY(need(h, lp + "attention.v_proj.weight", {H, H}, &wv));
+        TRY(need(h, lp + "attention.q_proj.bias", {H}, &bq));
+        TRY(need(h, lp + "attention.k_proj.bias", {H}, &bk));
+        TRY(need(h, lp + "attention.v_proj.bias", {H}, &bv));
+        TRY(need(h, lp + "attention.out_proj.weight", {H, H}, &wo));
+        TRY(need(h, lp + "attention.out_proj.bias", {H}, &bo));
+        TRY(need(h, lp + "feed_forward.intermediate_dense.weight", {F, H}, &w1));
+        TRY(need(h, lp + "feed_forward.intermediate_dense.bias", {F}, &b1));
+        TRY(need(h, lp + "feed_forward.output_dense.weight", {H, F}, &w2));
+        TRY(need(h, lp + "feed_forward.output_dense.bias", {H}, &b2));
+        LayerW& lw = h->layers[l];
+        TRY(need(h, lp + "layer_norm.weight", {H}, &lw.ln1_g));
+        TRY(need(h, lp + "layer_norm.bias", {H}, &lw.ln1_b));
+        TRY(need(h, lp + "final_layer_norm.weight", {H}, &lw.ln2_g));
+        TRY(need(h, lp + "final_layer_norm.bias", {H}, &lw.ln2_b));
+        // fused [q*0.125 ; k ; v]: the q scaling (head_dim^-0.5, applied after the bias, networks.py:162) is a power of two -> exact
+        float *wqkv, *bqkv;
+        const size_t hh = static_cast<size_t>(H) * H;
+        TRY(dev_alloc_t(h, h->owned, &wqkv, 3 * hh));
+        TRY(dev_alloc_t(h, h->owned, &bqkv, 3 * static_cast<size_t>(H)));
+        k_scale_copy<<<grid_for(hh), 256>>>(wq, wqkv, hh, 0.125f);
+        k_scale_copy<<<grid_for(hh), 256>>>(wk, wqkv + hh, hh, 1.0f);
+        k_scale_copy<<<grid_for(hh), 256>>>(wv, wqkv + 2 * hh, hh, 1.0f);
+        k_scale_copy<<<grid_for(H), 256>>>(bq, bqkv, H, 0.125f);
+        k_scale_copy<<<grid_for(H), 256>>>(bk, bqkv + H, H, 1.0f);
+        k_scale_copy<<<grid_for(H), 256>>>(bv, bqkv + 2 * H, H, 1.0f);
+        CKL();
+        TRY(make_lin(h, &lw.qkv, wqkv, bqkv, 3 * H, H));
+        TRY(make_lin(h, &lw.o, wo, bo, H, H));
+        TRY(make_lin(h, &lw.f1, w1, b1, F, H));
+        TRY(make_lin(h, &lw.f2, w2, b2, H, F));
+    }
+    h->skip.resize(nl / 2);
+    for (int m = 0; m < nl / 2; ++m) {
+        const std::string sp = p + "skip_connections_layers." + std::to_string(m) + ".";
+        const float *w, *b;
+        TRY(need(h, sp + "weight", {H, 2 * H}, &w));
+        TRY(need(h, sp + "bias", {H}, &b));
+        TRY(make_lin(h, &h->skip[m], w, b, H, 2 * H));
+    }
+    TRY(need(h, p + "proj_out.weight", {nf, H, 1}, &h->w_out));
+    TRY(need(h, p + "proj_out.bias", {nf}, &h->b_out));
+    CK(cudaDeviceSynchronize());
+    h->finalized = true;
+    return TVB_OK;
+}
+
+extern "C" int tvb_set_precision(tvb_handle* h, int32_t precision) {
+    if (!h) return fail(TVB_ERR_INVALID, "null handle");
+    if (precision != TVB_PRECISION_BF16 && precision != TVB_PRECISION_FP32_VALIDATE) return fail(TVB_ERR_INVALID, "unknown precision %d", precision);
+    h->precision = precision;
+    return TVB_OK;
+}
+extern "C" int tvb_get_precision(const tvb_handle* h) { return h ? h->precision : TVB_ERR_INVALID; }
+extern "C" int64_t tvb_kernel_launches(const tvb_handle* h) { return h ? h->launches : 0; }
+extern "C" int64_t tvb_device_bytes(const tvb_handle* h) { return h ? static_cast<int64_t>(h->dev_bytes + h->ws_bytes) : 0; }
+extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
+    if (!h || !name) return fail(TVB_ERR_INVALID, "null argument");
+    if (!strcmp(name, "attn_tc")) h->opt_attn_tc = value ? 1 : 0;
+    else if (!strcmp(name, "conv_tc")) h->opt_conv_tc = value ? 1 : 0;
+    else return fail(TVB_ERR_INVALID, "unknown option %s", name);
+    return TVB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// plan: packed row layout + workspace
+// ----------------------------------------------------------------------------------------------------------------
+static int alloc_act(tvb_handle* h, Act* a, int rows, int C, bool bf) {
+    a->C = C;
+    a->f32 = nullptr;
+    a->b16 = nullptr;
+    if (bf) {
+        TRY(dev_alloc_t(h, h->ws_owned, &a->b16, static_cast<size_t>(rows) * C));
+        CK(cudaMemset(a->b16, 0, static_cast<size_t>(rows) * C * sizeof(bf16)));
+    } else {
+        TRY(dev_alloc_t(h, h->ws_owned, &a->f32, static_cast<size_t>(rows) * C));
+        CK(cudaMemset(a->f32, 0, static_cast<size_t>(rows) * C * sizeof(float)));
+    }
+    return TVB_OK;
+}
+static int alloc_f32(tvb_handle* h, float** p, size_t n) {
+    TRY(dev_alloc_t(h, h->ws_owned, p, n));
+    CK(cudaMemset(*p, 0, n * sizeof(float)));
+    return TVB_OK;
+}
+
+static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int cfg_double, cudaStream_t st) {
+    const tvb_config& c = h->cfg;
+    if (!h->finalized) return fail(TVB_ERR_STATE, "tvb_finalize_weights has not been called");
+    if (B <= 0 || T <= 0) return fail(TVB_ERR_INVALID, "B and T must be positive");
+    const int H = c.hidden_size, F = c.intermediate_size, nf = c.n_feats, nl = c.num_hidden_layers;
+    const int GAP = 16;
+    std::vector<int> off(B);
+    int64_t o = 0;
+    for (int b = 0; b < B; ++b) {
+        if (lengths[b] < 0 || lengths[b] > T) return fail(TVB_ERR_INVALID, "lengths[%d] = %lld outside [0, T=%d]", b, (long long)lengths[b], T);
+        off[b] = static_cast<int>(o);
+        o += lengths[b] + 1 + GAP;
+    }
+    if (o > (1ll << 30)) return fail(TVB_ERR_INVALID, "batch too large");
+    const int half = static_cast<int>((o + 127) / 128 * 128);
+    const int nhalf = cfg_double ? 2 : 1;
+    const int Mp = half * nhalf;
+    const int nseq = B * nhalf;
+    std::vector<int> row_seq(Mp, -1), row_pos(Mp, 0), seqinfo(4 * static_cast<size_t>(nseq));
+    std::vector<int2> work16;
+    std::vector<int4> work128;
+    for (int s = 0; s < nseq; ++s) {
+        const int b = s % B;
+        const int uncond = cfg_double ? (s < B) : 0;
+        const int start = (s / B) * half + off[b];
+        const int len = static_cast<int>(lengths[b]) + 1;
+        seqinfo[s] = start;
+        seqinfo[nseq + s] = len;
+        seqinfo[2 * nseq + s] = b;
+        seqinfo[3 * nseq + s] = uncond;
+        for (int i = 0; i < len; ++i) { row_seq[start + i] = s; row_pos[start + i] = i; }
+        for (int q0 = 0; q0 < len; q0 += 16) work16.push_back(make_int2(s, q0));
+        for (int q0 = 0; q0 < len; q0 += 128) work128.push_back(make_int4(s, q0, start, len));
+    }
+    // ---- workspace (re)allocation
+    const bool bf = h->precision == TVB_PRECISION_BF16;
+    const size_t state_n = static_cast<size_t>(B) * nf * T;
+    if (Mp > h->ws_cap_rows || h->ws_precision != h->precision || state_n > h->ws_cap_state || nseq > h->seq_cap ||
+        (int)work16.size() > h->work16_cap || (int)work128.size() > h->work128_cap) {
+        CK(cudaStreamSynchronize(st));
+        CK(cudaDeviceSynchronize());
+        for (void* p : h->ws_owned) cudaFree(p);
+        h->ws_owned.clear();
+        h->ws_bytes = 0;
+        const int rows = Mp > h->ws_cap_rows ? Mp : h->ws_cap_rows;
+        const size_t sn = state_n > h->ws_cap_state ? state_n : h->ws_cap_state;
+        const int sc = nseq > h->seq_cap ? nseq : h->seq_cap;
+        const int w16c = (int)work16.size() > h->work16_cap ? (int)work16.size() : h->work16_cap;
+        const int w128c = (int)work128.size() > h->work128_cap ? (int)work128.size() : h->work128_cap;
+        TRY(dev_alloc_t(h, h->ws_owned, &h->d_row_seq, rows));
+        TRY(dev_alloc_t(h, h->ws_owned, &h->d_row_pos, rows));
+        TRY(dev_alloc_t(h, h->ws_owned, &h->d_seq, 4 * static_cast<size_t>(sc)));
+        TRY(dev_alloc_t(h, h->ws_owned, &h->d_work16, w16c));
+        TRY(dev_alloc_t(h, h->ws_owned, &h->d_work128, w128c));
+        TRY(dev_alloc_t(h, h->ws_owned, &h->d_tseq, sc));
+        TRY(alloc_f32(h, &h->base, static_cast<size_t>(rows) * H));
+        TRY(alloc_f32(h, &h->xpre, static_cast<size_t>(rows) * H));
+        TRY(alloc_f32(h, &h->hres, static_cast<size_t>(rows) * H));
+        TRY(alloc_f32(h, &h->vbuf, static_cast<size_t>(rows) * nf));
+        TRY(alloc_f32(h, &h->z_work, sn));
+        TRY(alloc_f32(h, &h->z_hat, sn));
+        TRY(alloc_f32(h, &h->v_pred, sn));
+        TRY(alloc_act(h, &h->hin, rows, H, false));                    // fp32 conv residual, always
+        if (bf) {
+            TRY(dev_alloc_t(h, h->ws_owned, &h->hin.b16, static_cast<size_t>(rows) * H));
+            CK(cudaMemset(h->hin.b16, 0, static_cast<size_t>(rows) * H * sizeof(bf16)));
+        }
+        TRY(alloc_act(h, &h->p1, rows, H, bf));
+        for (int i = 0; i < nl / 2; ++i) TRY(alloc_act(h, &h->slots[i], rows, H, bf));
+        TRY(alloc_act(h, &h->hbA, rows, H, bf));
+        TRY(alloc_act(h, &h->hbB, rows, H, bf));
+        TRY(alloc_act(h, &h->qkv, rows, 3 * H, bf));
+        TRY(alloc_act(h, &h->ctx, rows, H, bf));
+        TRY(alloc_act(h, &h->mid, rows, F, bf));
+        h->ws_cap_rows = rows;
+        h->ws_cap_state = sn;
+        h->seq_cap = sc;
+        h->work16_cap = w16c;
+        h->work128_cap = w128c;
+        h->ws_precision = h->precision;
+    }
+    CK(cudaMemcpyAsync(h->d_row_seq, row_seq.data(), sizeof(int) * Mp, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_row_pos, row_pos.data(), sizeof(int) * Mp, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_seq, seqinfo.data(), sizeof(int) * seqinfo.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_work16, work16.data(), sizeof(int2) * work16.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_work128, work128.data(), sizeof(int4) * work128.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));   // host vectors go out of scope
+    h->n_work16 = static_cast<int>(work16.size());
+    h->n_work128 = static_cast<int>(work128.size());
+    h->L.Mp = Mp;
+    h->L.nseq = nseq;
+    h->L.row_seq = h->d_row_seq;
+    h->L.row_pos = h->d_row_pos;
+    h->L.seq_start = h->d_seq;
+    h->L.seq_len = h->d_seq + nseq;
+    h->L.seq_utt = h->d_seq + 2 * nseq;
+    h->L.seq_uncond = h->d_seq + 3 * nseq;
+    h->plan_B = B; h->plan_T = T; h->plan_cfg = cfg_double; h->plan_half = half;
+    if (bf) {   // A-operand maps cover exactly the Mp live rows: TMA zero-fills anything outside
+        TRY(make_tmap(&h->hin.tm, h->hin.b16, Mp, H, H, 128));
+        TRY(make_tmap(&h->p1.tm, h->p1.b16, Mp, H, H, 128));
+        for (int i = 0; i < nl / 2; ++i) TRY(make_tmap(&h->slots[i].tm, h->slots[i].b16, Mp, H, H, 128));
+        TRY(make_tmap(&h->hbA.tm, h->hbA.b16, Mp, H, H, 128));
+        TRY(make_tmap(&h->hbB.tm, h->hbB.b16, Mp, H, H, 128));
+        TRY(make_tmap(&h->qkv.tm, h->qkv.b16, Mp, 3 * H, 3 * H, 128));
+        TRY(make_tmap(&h->ctx.tm, h->ctx.b16, Mp, H, H, 128));
+        TRY(make_tmap(&h->mid.tm, h->mid.b16, Mp, F, F, 128));
+    }
+    return TVB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// kernel launch helpers
+// ----------------------------------------------------------------------------------------------------------------
+static bool g_gemm_attr_set = false;
+template <int EPI>
+static int launch_gemm_tc_t(tvb_handle* h, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const GemmParams& p,
+                            cudaStream_t st, int num_sms) {
+    static bool attr = false;
+    if (!attr) {
+        CK(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+        attr = true;
+    }
+    const int tiles = (p.M / GEMM_BM) * (p.N / GEMM_BN);
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    gemm_tc_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(tmA, tmA2, tmB, p);
+    if (h) h->launches++;
+    CKL();
+    return TVB_OK;
+}
+static int launch_gemm_tc(tvb_handle* h, int epi, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
+                          const GemmParams& p, cudaStream_t st, int num_sms) {
+    if (p.M % GEMM_BM || p.N % GEMM_BN || p.K % GEMM_BK || p.K1 % GEMM_BK) return fail(TVB_ERR_INVALID, "gemm shape %dx%dx%d not tileable", p.M, p.N, p.K);
+    switch (epi) {
+        case EPI_BF16: return launch_gemm_tc_t<EPI_BF16>(h, tmA, tmA2, tmB, p, st, num_sms);
+        case EPI_GELU_BF16: return launch_gemm_tc_t<EPI_GELU_BF16>(h, tmA, tmA2, tmB, p, st, num_sms);
+        case EPI_RESID_F32: return launch_gemm_tc_t<EPI_RESID_F32>(h, tmA, tmA2, tmB, p, st, num_sms);
+        case EPI_DUAL: return launch_gemm_tc_t<EPI_DUAL>(h, tmA, tmA2, tmB, p, st, num_sms);
+        case EPI_F32: return launch_gemm_tc_t<EPI_F32>(h, tmA, tmA2, tmB, p, st, num_sms);
+    }
+    return fail(TVB_ERR_INVALID, "unknown epilogue %d", epi);
+}
+
+enum LinEpi { LE_PLAIN, LE_GELU, LE_RESID, LE_DUAL };
+// y = [a | a2] W^T + b with the epilogue the call site needs, in the active precision.
+//   LE_PLAIN: -> out (Act)          LE_GELU: -> gelu -> out (Act)
+//   LE_RESID: -> + resid -> out_f32 LE_DUAL: -> out_f32 and out (Act)
+static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, LinEpi epi, Act* out, const float* resid, float* out_f32,
+                  cudaStream_t st) {
+    const int Mp = h->L.Mp;
+    if (h->precision == TVB_PRECISION_BF16) {
+        GemmParams p{};
+        p.M = Mp; p.N = lin.N; p.K = lin.K; p.K1 = a2 ? a.C : lin.K;
+        p.bias = lin.bias; p.resid = resid; p.out_f32 = out_f32; p.out_bf16 = out ? out->b16 : nullptr; p.ld_out = lin.N;
+        const int e = epi == LE_PLAIN ? EPI_BF16 : epi == LE_GELU ? EPI_GELU_BF16 : epi == LE_RESID ? EPI_RESID_F32 : EPI_DUAL;
+        return launch_gemm_tc(h, e, a.tm, a2 ? a2->tm : a.tm, lin.tm, p, st, h->num_sms);
+    }
+    SgemmParams p{};
+    p.M = Mp; p.N = lin.N; p.K = lin.K; p.K1 = a2 ? a.C : lin.K;
+    p.A = a.f32; p.lda = a.C; p.A2 = a2 ? a2->f32 : a.f32; p.lda2 = a2 ? a2->C : a.C;
+    p.W = lin.w32; p.ldw = lin.K; p.bias = lin.bias; p.resid = resid; p.ldr = lin.N; p.alpha = 1.0f;
+    p.C = (epi == LE_RESID || epi == LE_DUAL) ? out_f32 : out->f32; p.ldc = lin.N;
+    if (epi == LE_GELU) TRY(launch_sgemm<SG_GELU>(h, p, st));
+    else if (epi == LE_RESID) TRY(launch_sgemm<SG_RESID>(h, p, st));
+    else TRY(launch_sgemm<SG_PLAIN>(h, p, st));
+    if (epi == LE_DUAL && out && out->f32 != out_f32)
+        CK(cudaMemcpyAsync(out->f32, out_f32, sizeof(float) * static_cast<size_t>(Mp) * lin.N, cudaMemcpyDeviceToDevice, st));
+    return TVB_OK;
+}
+
+static int layernorm(tvb_handle* h, const float* x, float* y, Act* yb, const float* g, const float* b, cudaStream_t st) {
+    const int Mp = h->L.Mp, H = h->cfg.hidden_size;
+    if (h->precision == TVB_PRECISION_BF16)
+        k_layernorm<bf16><<<(Mp + 7) / 8, 256, 0, st>>>(x, y, yb ? yb->b16 : nullptr, g, b, h->L.row_seq, Mp, H, 1e-5f);
+    else
+        k_layernorm<float><<<(Mp + 7) / 8, 256, 0, st>>>(x, y, yb ? yb->f32 : nullptr, g, b, h->L.row_seq, Mp, H, 1e-5f);
+    h->launches++;
+    CKL();
+    return TVB_OK;
+}
+
+static int attention(tvb_handle* h, cudaStream_t st) {
+    const int H = h->cfg.hidden_size, nh = h->cfg.num_attention_heads;
+    if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc) {
+        CK(launch_attn_tc_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, st));
+    } else if (h->precision == TVB_PRECISION_BF16) {
+        dim3 grid(h->n_work16, nh);
+        k_attn_simt<bf16><<<grid, 128, 0, st>>>(h->qkv.b16, h->ctx.b16, h->L, H, h->slopes, h->d_work16);
+    } else {
+        dim3 grid(h->n_work16, nh);
+        k_attn_simt<float><<<grid, 128, 0, st>>>(h->qkv.f32, h->ctx.f32, h->L, H, h->slopes, h->d_work16);
+    }
+    h->launches++;
+    CKL();
+    return TVB_OK;
+}
+
+static int posconv(tvb_handle* h, int i, bool last, cudaStream_t st) {
+    const tvb_config& c = h->cfg;
+    const int Mp = h->L.Mp, H = c.hidden_size, taps = c.convpos_width;
+    const bool bf = h->precision == TVB_PRECISION_BF16;
+    const bool first = (i == 0);
+    if (bf && h->opt_conv_tc) {
+        // in: hin (first) or p1; out: p1 bf16 (not last) or xpre fp32 = gelu*mask + hin (last)
+        const CUtensorMap& tin = first ? h->hin.tm : h->p1.tm;
+        CK(launch_conv_tc_raw(tin, h->conv_tm[i], h->conv_bias[i], h->L.row_seq, Mp, H, taps, c.convpos_groups,
+                              last ? nullptr : h->p1.b16, last ? h->xpre : nullptr, last ? h->hin.f32 : nullptr, h->num_sms, st));
+        h->launches++;
+        return TVB_OK;
+    }
+    dim3 grid((Mp + PC_ROWS - 1) / PC_ROWS, c.convpos_groups);
+    const size_t smem = static_cast<size_t>(PC_ROWS + taps - 1) * 64 * sizeof(float);
+    if (bf) {
+        const bf16* inb = first ? h->hin.b16 : h->p1.b16;
+        if (last)
+            k_posconv_simt<bf16, float, 1><<<grid, 256, smem, st>>>(inb, h->xpre, h->hin.f32, h->conv_wp32[i], h->conv_bias[i], h->L.row_seq, Mp, H, taps);
+        else
+            k_posconv_simt<bf16, bf16, 0><<<grid, 256, smem, st>>>(inb, h->p1.b16, nullptr, h->conv_wp32[i], h->conv_bias[i], h->L.row_seq, Mp, H, taps);
+        h->launches++;
+        CKL();
+        return TVB_OK;
+    }
+    const float* in = first ? h->hin.f32 : h->p1.f32;
+    if (last)
+        k_posconv_simt<float, float, 1><<<grid, 256, smem, st>>>(in, h->xpre, h->hin.f32, h->conv_wp32[i], h->conv_bias[i], h->L.row_seq, Mp, H, taps);
+    else
+        k_posconv_simt<float, float, 0><<<grid, 256, smem, st>>>(in, h->p1.f32, nullptr, h->conv_wp32[i], h->conv_bias[i], h->L.row_seq, Mp, H, taps);
+    h->launches++;
+    CKL();
+    return TVB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// one estimator pass over the planned rows (networks.py:302-374). Leaves W_out h + b in vbuf[row, :].
+// ----------------------------------------------------------------------------------------------------------------
+static int prep_base(tvb_handle* h, const int64_t* x, const float* cond, int cond_is_zero, cudaStream_t st) {
+    const tvb_config& c = h->cfg;
+    const size_t smem = static_cast<size_t>(c.n_feats) * FP_ROWS * sizeof(float);
+    k_frame_proj<true><<<h->L.Mp / FP_ROWS, 256, smem, st>>>(h->L, h->plan_T, c.n_feats, c.hidden_size, h->Wc_t, cond, x, h->G, h->b_in,
+                                                             c.n_tokens, cond_is_zero, nullptr, nullptr, 0.f, nullptr, h->base, nullptr);
+    h->launches++;
+    CKL();
+    return TVB_OK;
+}
+
+static int run_estimator(tvb_handle* h, const float* y, const float* t_seq_dev, float t_uniform, cudaStream_t st) {
+    const tvb_config& c = h->cfg;
+    const int Mp = h->L.Mp, H = c.hidden_size, nl = c.num_hidden_layers, nf = c.n_feats;
+    const bool bf = h->precision == TVB_PRECISION_BF16;
+    const size_t smem = static_cast<size_t>(nf) * FP_ROWS * sizeof(float);
+    k_frame_proj<false><<<Mp / FP_ROWS, 256, smem, st>>>(h->L, h->plan_T, nf, H, h->Wy_t, y, nullptr, nullptr, nullptr, 0, 0, h->base,
+                                                         t_seq_dev, t_uniform, h->freqs, h->hin.f32, bf ? h->hin.b16 : nullptr);
+    h->launches++;
+    CKL();
+    for (int i = 0; i < c.convpos_depth; ++i) TRY(posconv(h, i, i == c.convpos_depth - 1, st));
+    TRY(layernorm(h, h->xpre, h->hres, &h->slots[0], h->ln0_g, h->ln0_b, st));
+
+    int sp = 1;                       // skip stack pointer: slots[0..sp) are live
+    const Act* cur = &h->slots[0];    // bf16/fp32 copy of the current layer input
+    for (int l = 0; l < nl; ++l) {
+        const LayerW& lw = h->layers[l];
+        if (l >= nl / 2) {            // U-Net merge: Linear(2H -> H)([h ; skip]) as a two-operand split-K GEMM (networks.py:361-363)
+            const Act* skip = &h->slots[--sp];
+            TRY(linear(h, h->skip[l - nl / 2], *cur, skip, LE_DUAL, &h->hbB, nullptr, h->hres, st));
+            cur = &h->hbB;
+        }
+        TRY(linear(h, lw.qkv, *cur, nullptr, LE_PLAIN, &h->qkv, nullptr, nullptr, st));
+        TRY(attention(h, st));
+        TRY(linear(h, lw.o, h->ctx, nullptr, LE_RESID, nullptr, h->hres, h->xpre, st));
+        TRY(layernorm(h, h->xpre, h->hres, &h->hbB, lw.ln1_g, lw.ln1_b, st));
+        TRY(linear(h, lw.f1, h->hbB, nullptr, LE_GELU, &h->mid, nullptr, nullptr, st));
+        TRY(linear(h, lw.f2, h->mid, nullptr, LE_RESID, nullptr, h->hres, h->xpre, st));
+        Act* dst = (l < nl / 2 - 1) ? &h->slots[sp++] : &h->hbA;
+        TRY(layernorm(h, h->xpre, h->hres, dst, lw.ln2_g, lw.ln2_b, st));
+        cur = dst;
+    }
+    // output projection H -> n_feats on the fp32 residual stream (networks.py:372)
+    SgemmParams p{};
+    p.M = Mp; p.N = nf; p.K = H; p.K1 = H;
+    p.A = h->hres; p.lda = H; p.A2 = h->hres; p.lda2 = H;
+    p.W = h->w_out; p.ldw = H; p.bias = h->b_out; p.resid = nullptr; p.ldr = 0; p.C = h->vbuf; p.ldc = nf; p.alpha = 1.0f;
+    TRY(launch_sgemm<SG_PLAIN>(h, p, st));
+    return TVB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// public compute entry points
+// ----------------------------------------------------------------------------------------------------------------
+extern "C" int tvb_estimator_forward(tvb_handle* h, const int64_t* x_dev, const float* y_dev, const float* cond_dev, const float* t_host,
+                                     const int64_t* lengths_host, int32_t B, int32_t T, float* out_v_dev, void* stream) {
+    if (!h || !x_dev || !y_dev || !cond_dev || !t_host || !lengths_host || !out_v_dev) return fail(TVB_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TRY(build_plan(h, B, T, lengths_host, 0, st));
+    CK(cudaMemcpyAsync(h->d_tseq, t_host, sizeof(float) * B, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    TRY(prep_base(h, x_dev, cond_dev, 0, st));
+    TRY(run_estimator(h, y_dev, h->d_tseq, 0.f, st));
+    const size_t n = static_cast<size_t>(B) * h->cfg.n_feats * T;
+    k_scatter_velocity<<<grid_for(n), 256, 0, st>>>(h->vbuf, h->cfg.n_feats, h->L, h->cfg.n_feats, T, out_v_dev);
+    h->launches++;
+    CKL();
+    return TVB_OK;
+}
+
+static int ode_update(tvb_handle* h, const OdeParams& p, cudaStream_t st) {
+    const size_t n = static_cast<size_t>(p.B) * p.nf * p.T;
+    k_ode_update<<<grid_for(n), 256, 0, st>>>(h->vbuf, h->cfg.n_feats, h->L, p);
+    h->launches++;
+    CKL();
+    return TVB_OK;
+}
+
+extern "C" int tvb_sample_cfg(tvb_handle* h, const int64_t* x_dev, const float* z_dev, const float* cond_dev, const int64_t* lengths_host,
+                              int32_t B, int32_t T, float t, float gradient_scale, int32_t speech_prompt, float* out_v_dev, void* stream) {
+    if (!h || !x_dev || !z_dev || !cond_dev || !lengths_host || !out_v_dev) return fail(TVB_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int cfg = gradient_scale > 0.f ? 1 : 0;
+    TRY(build_plan(h, B, T, lengths_host, cfg, st));
+    TRY(prep_base(h, x_dev, cond_dev, speech_prompt ? 0 : 1, st));
+    TRY(run_estimator(h, z_dev, nullptr, t, st));
+    OdeParams p{};
+    p.B = B; p.nf = h->cfg.n_feats; p.T = T; p.cfg = cfg; p.g = gradient_scale; p.dt = 0.f; p.t_next = 0.f; p.P = 0;
+    p.one_minus_sigma = static_cast<float>(1.0 - static_cast<double>(h->cfg.sigma_min));
+    p.z_base = z_dev; p.v_prev = nullptr; p.eps = nullptr; p.cond = cond_dev; p.z_out = h->z_hat; p.v_out = out_v_dev;
+    return ode_update(h, p, st);
+}
+
+extern "C" int tvb_solve(tvb_handle* h, int32_t solver, const int64_t* x_dev, const float* z0_dev, const float* cond_dev,
+                         const int64_t* lengths_host, int32_t B, int32_t T, int32_t prompt_len, int32_t n_steps, const float* t_span_host,
+                         float gradient_scale, int32_t speech_prompt, const float* prompt_noise_dev, float* out_mel_dev, float* step_v_dev,
+                         void* stream) {
+    if (!h || !x_dev || !z0_dev || !cond_dev || !lengths_host || !t_span_host || !out_mel_dev) return fail(TVB_ERR_INVALID, "null argument");
+    if (solver != TVB_SOLVER_EULER && solver != TVB_SOLVER_HEUN) return fail(TVB_ERR_INVALID, "unknown solver %d", solver);
+    if (n_steps < 1) return fail(TVB_ERR_INVALID, "n_steps must be >= 1");
+    if (prompt_len < 0 || prompt_len > T) return fail(TVB_ERR_INVALID, "prompt_len %d outside [0, T]", prompt_len);
+    const int P = speech_prompt ? prompt_len : 0;
+    if (P > 0 && !prompt_noise_dev) return fail(TVB_ERR_INVALID, "prompt_noise_dev is required when speech_prompt and prompt_len > 0");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int cfg = gradient_scale > 0.f ? 1 : 0;
+    TRY(build_plan(h, B, T, lengths_host, cfg, st));
+    TRY(prep_base(h, x_dev, cond_dev, speech_prompt ? 0 : 1, st));
+    const size_t n = static_cast<size_t>(B) * h->cfg.n_feats * T;
+    CK(cudaMemcpyAsync(h->z_work, z0_dev, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+
+    OdeParams p{};
+    p.B = B; p.nf = h->cfg.n_feats; p.T = T; p.cfg = cfg; p.g = gradient_scale; p.P = P;
+    p.one_minus_sigma = static_cast<float>(1.0 - static_cast<double>(h->cfg.sigma_min));
+    p.cond = cond_dev;
+    // fp32 host arithmetic on t / dt exactly as the reference's 0-dim fp32 tensors (voicebox.py:75, :87, :96)
+    volatile float t = t_span_host[0];
+    volatile float dt = t_span_host[1] - t_span_host[0];
+    int noise_i = 0, eval_i = 0;
+    for (int step = 1; step <= n_steps; ++step) {
+        TRY(run_estimator(h, h->z_work, nullptr, t, st));
+        const float t_next = t + dt;
+        const bool corrector = (solver == TVB_SOLVER_HEUN) && (step < n_steps);
+        p.dt = dt; p.t_next = t_next;
+        p.z_base = h->z_work; p.v_prev = nullptr;
+        p.eps = P > 0 ? prompt_noise_dev + static_cast<size_t>(noise_i++) * n : nullptr;
+        p.z_out = corrector ? h->z_hat : h->z_work;
+        p.v_out = corrector ? h->v_pred : (step_v_dev ? step_v_dev + static_cast<size_t>(eval_i) * n : nullptr);
+        TRY(ode_update(h, p, st));
+        if (corrector && step_v_dev)
+            CK(cudaMemcpyAsync(step_v_dev + static_cast<size_t>(eval_i) * n, h->v_pred, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        ++eval_i;
+        t = t_next;
+        if (corrector) {
+            TRY(run_estimator(h, h->z_hat, nullptr, t, st));
+            p.z_base = h->z_work; p.v_prev = h->v_pred;
+            p.eps = P > 0 ? prompt_noise_dev + static_cast<size_t>(noise_i++) * n : nullptr;
+            p.z_out = h->z_work;
+            p.v_out = step_v_dev ? step_v_dev + static_cast<size_t>(eval_i) * n : nullptr;
+            TRY(ode_update(h, p, st));
+            ++eval_i;
+        }
+        if (step < n_steps) dt = t_span_host[step + 1] - t;
+    }
+    CK(cudaMemcpyAsync(out_mel_dev, h->z_work, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return TVB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// test hooks
+// ----------------------------------------------------------------------------------------------------------------
+extern "C" int tvb_debug_gemm_bf16(int device, const void* a_dev, const void* w_dev, const float* bias_dev, const float* resid_dev,
+                                   float* out_f32_dev, void* out_bf16_dev, int32_t M, int32_t N, int32_t K, int32_t epilogue, void* stream) {
+    if (!a_dev || !w_dev) return fail(TVB_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(TVB_ERR_INVALID, "sm_100a device required");
+    CUtensorMap tmA, tmB;
+    TRY(make_tmap(&tmA, a_dev, M, K, K, 128));
+    TRY(make_tmap(&tmB, w_dev, N, K, K, GEMM_BN));
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.K1 = K; p.bias = bias_dev; p.resid = resid_dev; p.out_f32 = out_f32_dev;
+    p.out_bf16 = static_cast<bf16*>(out_bf16_dev); p.ld_out = N;
+    return launch_gemm_tc(nullptr, epilogue, tmA, tmA, tmB, p, static_cast<cudaStream_t>(stream), prop.multiProcessorCount);
+}

@@ -1,0 +1,310 @@
+"""Drop-in host-side mirror of the reference decoder sampling API, backed by libtvb.so (sm_100a CUDA).
+
+Mirrors (same names, argument meaning and error behaviour):
+    reference src/decoder/voicebox/model/voicebox.py:16-176   CFM / Voicebox
+    reference src/decoder/voicebox/model/networks.py:270-374  Transformer (as `Voicebox.estimator`)
+The module tree below exists only to carry parameters under the reference's state-dict keys (so
+`load_state_dict` / `PyTorchModelHubMixin.from_pretrained` work unchanged); every forward computation happens in
+the CUDA library through the C ABI of include/tvb.h.  There is no PyTorch or CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import engine as E
+
+try:  # same mixin as the reference (voicebox.py:10,153); optional so that the package imports without it
+    from huggingface_hub import PyTorchModelHubMixin
+except Exception:  # pragma: no cover
+    class PyTorchModelHubMixin:  # type: ignore
+        pass
+
+
+# ------------------------------------------------------------------------------------------------------------
+# parameter containers with the reference's names / shapes / construction order (networks.py:67-85,119-147,
+# 214-223, 236-248, 270-300).  They define no forward().
+# ------------------------------------------------------------------------------------------------------------
+class _ConvPos(nn.Module):
+    def __init__(self, hidden, width, groups):
+        super().__init__()
+        conv = nn.Conv1d(hidden, hidden, kernel_size=width, padding=width // 2, groups=groups)
+        self.conv = nn.utils.parametrizations.weight_norm(conv, name="weight", dim=2)
+
+
+class _AttentionParams(nn.Module):
+    def __init__(self, hidden):
+        super().__init__()
+        self.k_proj = nn.Linear(hidden, hidden)
+        self.v_proj = nn.Linear(hidden, hidden)
+        self.q_proj = nn.Linear(hidden, hidden)
+        self.out_proj = nn.Linear(hidden, hidden)
+
+
+class _FeedForwardParams(nn.Module):
+    def __init__(self, hidden, inter):
+        super().__init__()
+        self.intermediate_dense = nn.Linear(hidden, inter)
+        self.output_dense = nn.Linear(inter, hidden)
+
+
+class _LayerParams(nn.Module):
+    def __init__(self, hidden, inter):
+        super().__init__()
+        self.attention = _AttentionParams(hidden)
+        self.layer_norm = nn.LayerNorm(hidden, eps=1e-5)
+        self.feed_forward = _FeedForwardParams(hidden, inter)
+        self.final_layer_norm = nn.LayerNorm(hidden, eps=1e-5)
+
+
+class Estimator(nn.Module):
+    """`Voicebox.estimator`: parameters of the reference Transformer + a CUDA forward (networks.py:302-374)."""
+
+    def __init__(self, owner: "Voicebox", n_feats, n_tokens, embedding_dim, hidden_size, intermediate_size,
+                 num_attention_heads, num_hidden_layers, convpos_width, convpos_groups, convpos_depth):
+        super().__init__()
+        object.__setattr__(self, "_owner", owner)      # not a submodule: avoid a reference cycle in state_dict
+        self.hidden_size = hidden_size
+        self.embedding_dim = embedding_dim
+        self.num_heads = num_attention_heads
+        self.num_hidden_layers = num_hidden_layers
+        self.embed = nn.Embedding(n_tokens, embedding_dim)
+        self.proj_in = nn.Conv1d(2 * n_feats + embedding_dim, hidden_size, kernel_size=1)
+        self.pos_conv_embeds = nn.ModuleList([_ConvPos(hidden_size, convpos_width, convpos_groups) for _ in range(convpos_depth)])
+        self.layer_norm = nn.LayerNorm(hidden_size, eps=1e-5)
+        self.layers = nn.ModuleList([_LayerParams(hidden_size, intermediate_size) for _ in range(num_hidden_layers)])
+        self.skip_connections_layers = nn.ModuleList([nn.Linear(2 * hidden_size, hidden_size) for _ in range(num_hidden_layers // 2)])
+        self.proj_out = nn.Conv1d(hidden_size, n_feats, kernel_size=1)
+
+    def forward(self, x, y, cond, t, lengths):
+        return self._owner._estimator_forward(x, y, cond, t, lengths)
+
+
+def _dev_ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Voicebox(nn.Module, PyTorchModelHubMixin):
+    """B200-native token-Voicebox.  Same constructor and sampling API as the reference `Voicebox` (voicebox.py:153-176).
+
+    Extensions over the reference: `generate` accepts batches (the reference's `sample` only works for B == 1,
+    voicebox.py:52) and `precision` selects the bf16 tensor-core path ("bf16", default) or the fp32 validation path.
+    """
+
+    def __init__(self, n_feats, n_tokens, embedding_dim, hidden_size, intermediate_size, num_attention_heads,
+                 num_hidden_layers, convpos_width, convpos_groups, convpos_depth, attention_dropout=0.0,
+                 activation_dropout=0.1, hidden_dropout=0.0, solver="euler", sigma_min=1e-4):
+        super().__init__()
+        self.solver = solver
+        self.sigma_min = sigma_min
+        self.n_tokens = n_tokens
+        self.n_feats = n_feats
+        # dropouts are accepted for signature compatibility; sampling runs in eval mode where they are identity
+        self._cfg = E.TvbConfig(n_feats, n_tokens, embedding_dim, hidden_size, intermediate_size, num_attention_heads,
+                                num_hidden_layers, convpos_width, convpos_groups, convpos_depth, float(sigma_min))
+        self.estimator = Estimator(self, n_feats, n_tokens + 1, embedding_dim, hidden_size, intermediate_size,
+                                   num_attention_heads, num_hidden_layers, convpos_width, convpos_groups, convpos_depth)
+        self._handle: Optional[C.c_void_p] = None
+        self._handle_device: Optional[int] = None
+        self._weights_version = 0
+        self._uploaded_version = -1
+        self._precision = E.PRECISION_BF16
+        self._options = {}
+
+    # ---- reference BaseModule API (model/base.py:13-37)
+    @property
+    def nparams(self):
+        return sum(int(np.prod(p.shape)) for p in self.parameters() if p.requires_grad)
+
+    def relocate_input(self, x: list):
+        device = next(self.parameters()).device
+        for i in range(len(x)):
+            if isinstance(x[i], torch.Tensor) and x[i].device != device:
+                x[i] = x[i].to(device)
+        return x
+
+    # ---- engine lifetime -------------------------------------------------------------------------------
+    def set_precision(self, precision: str) -> "Voicebox":
+        self._precision = {"bf16": E.PRECISION_BF16, "fp32": E.PRECISION_FP32_VALIDATE}[precision]
+        if self._handle is not None:
+            E.check(E.load_library().tvb_set_precision(self._handle, self._precision))
+        return self
+
+    def set_option(self, name: str, value: int) -> "Voicebox":
+        self._options[name] = int(value)
+        if self._handle is not None:
+            E.check(E.load_library().tvb_set_option(self._handle, name.encode(), int(value)))
+        return self
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self._weights_version += 1
+        return out
+
+    def _apply(self, fn, *a, **k):          # .to() / .cuda() / .float(): weights may have moved -> re-upload lazily
+        out = super()._apply(fn, *a, **k)
+        self._weights_version += 1
+        return out
+
+    def invalidate_weights(self) -> None:
+        """Call after mutating parameters in place so that the next call re-packs them on the device."""
+        self._weights_version += 1
+
+    def _release(self):
+        if self._handle is not None:
+            try:
+                E.load_library().tvb_destroy(self._handle)
+            except Exception:
+                pass
+            self._handle = None
+
+    def __del__(self):
+        self._release()
+
+    def _engine(self, device: torch.device):
+        lib = E.load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("usdm_b200 needs a CUDA (sm_100a) device; there is no CPU path")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if self._handle is not None and (self._handle_device != idx or self._uploaded_version != self._weights_version):
+            self._release()
+        if self._handle is None:
+            h = C.c_void_p()
+            E.check(lib.tvb_create(C.byref(self._cfg), idx, C.byref(h)))
+            self._handle, self._handle_device = h, idx
+            try:
+                for key, ten in self.state_dict().items():
+                    t = ten.detach().to(torch.float32).contiguous()
+                    shape = (C.c_int64 * t.dim())(*t.shape)
+                    E.check(lib.tvb_load_weight(h, key.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()))
+                E.check(lib.tvb_finalize_weights(h))
+                E.check(lib.tvb_set_precision(h, self._precision))
+                for k, v in self._options.items():
+                    E.check(lib.tvb_set_option(h, k.encode(), v))
+            except Exception:
+                self._release()
+                raise
+            self._uploaded_version = self._weights_version
+        return lib, self._handle
+
+    @staticmethod
+    def _prep(x, *floats):
+        if not floats[0].is_cuda:
+            raise RuntimeError("usdm_b200.Voicebox runs on CUDA tensors only (no CPU path); move inputs to the B200")
+        dev = floats[0].device
+        x = x.to(device=dev, dtype=torch.int64).contiguous()
+        fl = [None if f is None else f.to(device=dev, dtype=torch.float32).contiguous() for f in floats]
+        return (dev, x, *fl)
+
+    @staticmethod
+    def _host_lengths(lengths, B):
+        l = torch.as_tensor(lengths).detach().to("cpu", torch.int64).reshape(-1).contiguous()
+        if l.numel() != B:
+            raise ValueError(f"lengths has {l.numel()} entries for batch {B}")
+        return l, l.numpy().ctypes.data_as(C.POINTER(C.c_int64))
+
+    @staticmethod
+    def _stream(dev):
+        return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    # ---- Transformer.forward (networks.py:302-374) ------------------------------------------------------
+    @torch.no_grad()
+    def _estimator_forward(self, x, y, cond, t, lengths):
+        dev, x, y, cond = self._prep(x, y, cond)
+        B, M, T = y.shape
+        if x.shape != (B, T) or cond.shape != y.shape:
+            raise ValueError(f"shape mismatch: x {tuple(x.shape)}, y {tuple(y.shape)}, cond {tuple(cond.shape)}")
+        lib, h = self._engine(dev)
+        th = torch.as_tensor(t).detach().to("cpu", torch.float32).reshape(-1)
+        if th.numel() == 1:
+            th = th.expand(B)
+        th = th.contiguous()
+        if th.numel() != B:
+            raise ValueError("t must have one entry per batch element")
+        lh, lp = self._host_lengths(lengths, B)
+        out = torch.empty_like(y)
+        E.check(lib.tvb_estimator_forward(h, _dev_ptr(x), _dev_ptr(y), _dev_ptr(cond),
+                                          th.numpy().ctypes.data_as(C.POINTER(C.c_float)), lp, B, T, _dev_ptr(out), self._stream(dev)))
+        return out
+
+    # ---- CFM.sample (voicebox.py:51-72) -----------------------------------------------------------------
+    @torch.no_grad()
+    def sample(self, x, z, cond, cond_lengths, t, gradient_scale, speech_prompt):
+        dev, x, z, cond = self._prep(x, z, cond)
+        B, M, T = z.shape
+        lib, h = self._engine(dev)
+        lh, lp = self._host_lengths(cond_lengths, B)
+        tv = float(torch.as_tensor(t).detach().to("cpu", torch.float32).reshape(-1)[0])
+        out = torch.empty_like(z)
+        E.check(lib.tvb_sample_cfg(h, _dev_ptr(x), _dev_ptr(z), _dev_ptr(cond), lp, B, T, tv, float(gradient_scale),
+                                   int(bool(speech_prompt)), _dev_ptr(out), self._stream(dev)))
+        return out, 0
+
+    # ---- CFM.solve_euler / solve_heun (voicebox.py:74-138) ----------------------------------------------
+    def _solve(self, solver_id, x, z, cond, cond_lengths, t_span, gradient_scale, speech_prompt, prompt_lengths,
+               return_velocities=False, noises=None):
+        dev, x, z, cond = self._prep(x, z, cond)
+        B, M, T = z.shape
+        lib, h = self._engine(dev)
+        lh, lp = self._host_lengths(cond_lengths, B)
+        ts = torch.as_tensor(t_span).detach().to("cpu", torch.float32).contiguous()
+        n_steps = ts.numel() - 1
+        if n_steps < 1:
+            raise ValueError("t_span needs at least two entries")
+        n_evals = n_steps if solver_id == E.SOLVER_EULER else 2 * n_steps - 1
+        P = 0
+        noise = None
+        if speech_prompt:
+            if prompt_lengths is None:
+                raise TypeError("prompt_lengths is required when speech_prompt=True")   # reference: NoneType[0] -> TypeError
+            P = int(torch.as_tensor(prompt_lengths).reshape(-1)[0])                    # only element [0] is used (voicebox.py:92)
+            P = max(0, min(P, T))
+            if noises is not None:
+                noise = torch.stack([n.to(dev, torch.float32) for n in noises]).contiguous()
+            else:
+                # same call sequence as the reference: one full-shape randn_like(cond) per solver (sub)step
+                noise = torch.stack([torch.randn_like(cond) for _ in range(n_evals)])
+        out = torch.empty_like(z)
+        vel = torch.empty((n_evals, B, M, T), device=dev, dtype=torch.float32) if return_velocities else None
+        E.check(lib.tvb_solve(h, solver_id, _dev_ptr(x), _dev_ptr(z), _dev_ptr(cond), lp, B, T, P, n_steps,
+                              ts.numpy().ctypes.data_as(C.POINTER(C.c_float)), float(gradient_scale), int(bool(speech_prompt)),
+                              _dev_ptr(noise) if P > 0 else None, _dev_ptr(out), _dev_ptr(vel), self._stream(dev)))
+        if noise is not None:
+            noise.record_stream(torch.cuda.current_stream(dev))
+        return (out, vel) if return_velocities else out
+
+    @torch.no_grad()
+    def solve_euler(self, x, z, cond, cond_lengths, t_span, gradient_scale, speech_prompt, prompt_lengths, **kw):
+        return self._solve(E.SOLVER_EULER, x, z, cond, cond_lengths, t_span, gradient_scale, speech_prompt, prompt_lengths, **kw)
+
+    @torch.no_grad()
+    def solve_heun(self, x, z, cond, cond_lengths, t_span, gradient_scale, speech_prompt, prompt_lengths, **kw):
+        return self._solve(E.SOLVER_HEUN, x, z, cond, cond_lengths, t_span, gradient_scale, speech_prompt, prompt_lengths, **kw)
+
+    # ---- CFM.generate (voicebox.py:140-150) --------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, x, cond, cond_lengths, n_timesteps, solver="euler", gradient_scale=0.0, speech_prompt=False,
+                 prompt_lengths=None):
+        z = torch.randn_like(cond)
+        if solver == "heun":
+            n_timesteps = (n_timesteps + 1) // 2
+        t_span = torch.linspace(0, 1, n_timesteps + 1, device=cond.device).to(z)
+        if solver == "euler":
+            return self.solve_euler(x, z, cond, cond_lengths, t_span, gradient_scale, speech_prompt, prompt_lengths)
+        elif solver == "heun":
+            return self.solve_heun(x, z, cond, cond_lengths, t_span, gradient_scale, speech_prompt, prompt_lengths)
+        # unknown solver: the reference silently returns None (voicebox.py:147-150)
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("training loss (CFM.forward, voicebox.py:28-49) is out of scope of the sampling engine")
+
+    # ---- stats ---------------------------------------------------------------------------------------------
+    def kernel_launches(self) -> int:
+        return 0 if self._handle is None else int(E.load_library().tvb_kernel_launches(self._handle))
+
+    def device_bytes(self) -> int:
+        return 0 if self._handle is None else int(E.load_library().tvb_device_bytes(self._handle))
