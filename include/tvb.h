@@ -70,7 +70,8 @@ int tvb_finalize_weights(tvb_handle* h);
 int tvb_set_precision(tvb_handle* h, int32_t precision);
 int tvb_get_precision(const tvb_handle* h);
 /* Ablation / cross-check switches of the bf16 path: "attn_tc" and "conv_tc" (1 = tcgen05 kernel, default;
- * 0 = the CUDA-core kernel of the same op).  Both are GPU kernels of this library; there is no CPU path. */
+ * 0 = the CUDA-core kernel of the same op; both are GPU kernels of this library, there is no CPU path), and
+ * "profile" (see tvb_profile_read). */
 int tvb_set_option(tvb_handle* h, const char* name, int32_t value);
 
 /* Replaces: Transformer.forward(x, y, cond, t, lengths) (networks.py:302-374) — the per-step velocity estimator.
@@ -101,6 +102,13 @@ int tvb_solve(tvb_handle* h, int32_t solver, const int64_t* x_dev, const float* 
               const int64_t* lengths_host, int32_t B, int32_t T, int32_t prompt_len, int32_t n_steps,
               const float* t_span_host, float gradient_scale, int32_t speech_prompt,
               const float* prompt_noise_dev, float* out_mel_dev, float* step_v_dev, void* stream);
+
+/* Per-kernel timing (bench.py's roofline leg).  With tvb_set_option(h, "profile", 1) every kernel launch is bracketed by
+ * CUDA events on the launching stream; tvb_profile_read synchronises the device, sums the elapsed milliseconds and launch
+ * counts by category into two arrays of 8 entries and resets the log.
+ * Categories: 0 linear-layer GEMMs, 1 attention, 2 positional conv, 3 LayerNorm, 4 frame projection / time token,
+ * 5 output projection + CFG/ODE update, 6-7 unused. */
+int tvb_profile_read(tvb_handle* h, double* ms_by_cat, int64_t* launches_by_cat);
 
 /* Number of this library's kernels launched by the handle since creation (bench.py's gpu_launches). */
 int64_t tvb_kernel_launches(const tvb_handle* h);

@@ -1,0 +1,87 @@
+"""GPU: the bf16 tcgen05 path against the reference goldens / the oracle: per-step velocity rel-L2 <= 1e-2
+(BASELINE.json north_star), with each tensor-core kernel also cross-checked against its CUDA-core twin."""
+import pytest
+import torch
+
+from util import CFG, O, golden, max_abs, model, rel_l2, weights
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+def _est(m, g):
+    v = m.estimator(g["x"].cuda(), g["y"].cuda(), g["cond"].cuda(), g["t"], g["lengths"])
+    torch.cuda.synchronize()
+    return v
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("attn_tc,conv_tc", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_estimator_ragged_vs_reference_golden(attn_tc, conv_tc):
+    g = golden("estimator_ragged.pt")
+    m = model(0, True, "bf16")
+    m.set_option("attn_tc", attn_tc)
+    m.set_option("conv_tc", conv_tc)
+    v = _est(m, g)
+    err = rel_l2(v, g["v"])
+    print(f"bf16 estimator (attn_tc={attn_tc}, conv_tc={conv_tc}) rel-L2 vs reference fp32: {err:.3e}")
+    assert torch.isfinite(v).all()
+    assert err < TOL
+    for b, L in enumerate(g["lengths"].tolist()):
+        assert float(v[b, :, L:].abs().sum()) == 0.0
+
+
+@pytest.mark.timeout(900)
+def test_config1_teacher_forced_velocity_and_final_mel():
+    """configs[0]: all 3 stored steps teacher-forced (<= 1e-2), then the free-running 32-step solve (max-abs stated)."""
+    g = golden("config1_euler32.pt")
+    m = model(0, False, "bf16")
+    t_span = torch.linspace(0, 1, 33)
+    for idx, k in enumerate(g["steps"]):
+        t = t_span[0]; dt = t_span[1] - t_span[0]
+        for s in range(1, k + 1):
+            t = t + dt; dt = t_span[s + 1] - t
+        v, _ = m.sample(g["x"].cuda(), g["z_in"][idx].cuda(), g["cond"].cuda(), g["lengths"], t, 1.0, True)
+        torch.cuda.synchronize()
+        e = rel_l2(v, g["v"][idx])
+        print(f"config1 step {k}: bf16 velocity rel-L2 {e:.3e}")
+        assert e < TOL
+    torch.manual_seed(g["noise_seed"])
+    cond = g["cond"]
+    z0 = torch.randn_like(cond)
+    noises = [torch.randn_like(cond) for _ in range(32)]
+    out = m.solve_euler(g["x"].cuda(), z0.cuda(), cond.cuda(), g["lengths"], t_span, 1.0, True, torch.tensor([g["prompt_len"]]), noises=noises)
+    torch.cuda.synchronize()
+    P = g["prompt_len"]
+    print(f"config1 free-running final mel: max-abs err {max_abs(out[:, :, P:], g['final'][:, :, P:]):.4f}, rel-L2 {rel_l2(out[:, :, P:], g['final'][:, :, P:]):.3e}")
+    assert rel_l2(out, g["final"]) < 0.1
+
+
+@pytest.mark.timeout(900)
+def test_long_sequence_multi_block_attention():
+    """S > 128 keys so that the online-softmax rescale path and multiple KV blocks are exercised; oracle on the GPU."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    gen = torch.Generator().manual_seed(3)
+    B, T = 3, 700
+    x = torch.randint(0, 10000, (B, T), generator=gen)
+    y = torch.randn(B, 80, T, generator=gen)
+    cond = torch.randn(B, 80, T, generator=gen)
+    L = torch.tensor([700, 389, 130])
+    t = torch.tensor([0.05, 0.5, 0.95])
+    sd = {k: v.cuda() for k, v in weights(0, True).items()}
+    with torch.no_grad():
+        ref = O.estimator_forward(sd, CFG, x.cuda(), y.cuda(), cond.cuda(), t.cuda(), L.cuda())
+    m = model(0, True, "bf16")
+    v = m.estimator(x.cuda(), y.cuda(), cond.cuda(), t, L)
+    torch.cuda.synchronize()
+    for b in range(B):
+        e = rel_l2(v[b], ref[b])
+        print(f"seq {b} (len {int(L[b])}): rel-L2 {e:.3e}")
+        assert e < TOL
+    m.set_precision("fp32")
+    v32 = m.estimator(x.cuda(), y.cuda(), cond.cuda(), t, L)
+    torch.cuda.synchronize()
+    e32 = rel_l2(v32, ref)
+    print(f"fp32 validation path vs oracle(cuda fp32): {e32:.3e}")
+    assert e32 < 1e-5

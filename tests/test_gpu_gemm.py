@@ -1,0 +1,53 @@
+"""GPU: the tcgen05/TMA bf16 GEMM (usdm_b200/csrc/gemm_tc.cuh) against torch on the same bf16 operands."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(M, N, K, epi, seed=0):
+    from usdm_b200 import engine
+    lib = engine.load_library()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a = (torch.randn(M, K, device="cuda", generator=g)).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    of = torch.full((M, N), float("nan"), device="cuda")
+    ob = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    rc = lib.tvb_debug_gemm_bf16(0, p(a), p(w), p(bias), p(resid), p(of), p(ob), M, N, K, epi,
+                                 C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    engine.check(rc)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias
+    return ref, resid, of, ob
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (128, 256, 512), (1024, 1024, 1024),
+                                   (384, 3072, 1024), (256, 1024, 4096), (148 * 128 * 2 + 128, 1024, 1024)])
+def test_gemm_f32_epilogue(M, N, K):
+    ref, _, of, _ = _run(M, N, K, 4)
+    err = (of - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("epi", [0, 1, 2, 3])
+def test_gemm_epilogues(epi):
+    M, N, K = 512, 1024, 1024
+    ref, resid, of, ob = _run(M, N, K, epi, seed=epi + 1)
+    if epi == 0:
+        want = ref.to(torch.bfloat16).float(); got = ob.float()
+    elif epi == 1:
+        want = torch.nn.functional.gelu(ref).to(torch.bfloat16).float(); got = ob.float()
+    elif epi == 2:
+        want = ref + resid; got = of
+    else:
+        want = ref; got = of
+        assert (ob.float() - ref.to(torch.bfloat16).float()).abs().max().item() < 0.05
+    err = (got - want).abs().max().item()
+    assert err < 0.03, f"epilogue {epi}: max abs err {err}"

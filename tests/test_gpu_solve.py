@@ -1,0 +1,102 @@
+"""GPU: sampler-level behaviour through the public API (generate / solve_* / sample), bf16 path, oracle as checker."""
+import pytest
+import torch
+
+from util import CFG, O, golden, max_abs, model, rel_l2, weights
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(seed, B, T, lengths, P):
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randint(0, 10000, (B, T), generator=gen)
+    cond = torch.randn(B, 80, T, generator=gen)
+    cond[:, :, P:] = 0
+    return x, cond, torch.tensor(lengths)
+
+
+@pytest.mark.timeout(900)
+def test_generate_matches_oracle_noise_stream_and_shapes():
+    """generate() draws z and the per-step prompt noise from torch's CUDA generator in the reference's order."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x, cond, L = _inputs(5, 2, 96, [96, 57], 24)
+    m = model(0, True, "bf16")
+    torch.manual_seed(77)
+    out = m.generate(x.cuda(), cond.cuda(), L, 4, solver="euler", gradient_scale=0.7, speech_prompt=True, prompt_lengths=torch.tensor([24]))
+    torch.cuda.synchronize()
+    assert out.shape == cond.shape and out.dtype == torch.float32
+    sd = {k: v.cuda() for k, v in weights(0, True).items()}
+    torch.manual_seed(77)
+    cc = cond.cuda()
+    z0 = torch.randn_like(cc)
+    noises = [torch.randn_like(cc) for _ in range(4)]
+    with torch.no_grad():
+        ref = O.solve_euler(sd, CFG, x.cuda(), z0, cc, L.cuda(), torch.linspace(0, 1, 5, device="cuda"), 0.7, True, 24, noises)
+    e = rel_l2(out, ref)
+    print("generate vs oracle (same CUDA noise stream): rel-L2", e, "max-abs", max_abs(out, ref))
+    assert e < 2e-2
+    assert m.generate(x.cuda(), cond.cuda(), L, 4, solver="rk4") is None      # reference: unknown solver -> None
+
+
+@pytest.mark.timeout(900)
+def test_ragged_batch_equals_per_utterance_and_padding_is_ignored():
+    """ragged == trimmed per-utterance (reference: 7.7e-7) and padded-region garbage has no effect (reference: 0)."""
+    x, cond, L = _inputs(6, 3, 200, [200, 131, 64], 200)
+    gen = torch.Generator().manual_seed(9)
+    y = torch.randn(3, 80, 200, generator=gen)
+    t = torch.tensor([0.4, 0.4, 0.4])
+    m = model(0, True, "bf16")
+    v = m.estimator(x.cuda(), y.cuda(), cond.cuda(), t, L).clone()
+    # garbage in the padded region must not change anything, bit for bit
+    x2, y2, c2 = x.clone(), y.clone(), cond.clone()
+    for b, l in enumerate(L.tolist()):
+        x2[b, l:] = 1234; y2[b, :, l:] = 1e3; c2[b, :, l:] = -1e3
+    v2 = m.estimator(x2.cuda(), y2.cuda(), c2.cuda(), t, L)
+    torch.cuda.synchronize()
+    assert torch.equal(v, v2)
+    for b, l in enumerate(L.tolist()):
+        vb = m.estimator(x[b:b + 1, :l].cuda(), y[b:b + 1, :, :l].contiguous().cuda(), cond[b:b + 1, :, :l].contiguous().cuda(), t[b:b + 1], torch.tensor([l]))
+        torch.cuda.synchronize()
+        e = rel_l2(vb, v[b:b + 1, :, :l])
+        print(f"utt {b}: ragged vs alone rel-L2 {e:.3e}")
+        assert e < 1e-6, "each sequence is computed independently of its batch neighbours"
+
+
+@pytest.mark.timeout(900)
+def test_heun_and_cfg_off_and_prompt_off_vs_oracle():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x, cond, L = _inputs(7, 2, 80, [80, 41], 20)
+    sd = {k: v.cuda() for k, v in weights(0, True).items()}
+    m = model(0, True, "bf16")
+    for solver, gs, sp in [("heun", 1.0, True), ("heun", 0.0, False), ("euler", 0.0, True), ("euler", 1.5, False)]:
+        gen = torch.Generator().manual_seed(31)
+        z0 = torch.randn(cond.shape, generator=gen)
+        nt = 5
+        n = (nt + 1) // 2 if solver == "heun" else nt
+        noises = [torch.randn(cond.shape, generator=gen) for _ in range(O.n_noise_draws(solver, nt))]
+        t_span = torch.linspace(0, 1, n + 1)
+        fn = m.solve_euler if solver == "euler" else m.solve_heun
+        out = fn(x.cuda(), z0.cuda(), cond.cuda(), L, t_span, gs, sp, torch.tensor([20]), noises=noises if sp else None)
+        ofn = O.solve_euler if solver == "euler" else O.solve_heun
+        with torch.no_grad():
+            ref = ofn(sd, CFG, x.cuda(), z0.cuda(), cond.cuda(), L.cuda(), t_span.cuda(), gs, sp, 20, [n_.cuda() for n_ in noises])
+        torch.cuda.synchronize()
+        e = rel_l2(out, ref)
+        print(solver, gs, sp, "rel-L2", e)
+        assert e < 2e-2
+        # padded frames beyond the prompt: v == 0 there, so z0 is carried through unchanged, as in the reference
+        assert torch.equal(out[1, :, 41:].cpu(), z0[1, :, 41:]) and rel_l2(ref[1, :, 41:], z0[1, :, 41:]) < 1e-6
+
+
+@pytest.mark.timeout(900)
+def test_edge_cases_zero_length_and_single_frame():
+    x, cond, L = _inputs(8, 3, 32, [0, 1, 32], 32)
+    gen = torch.Generator().manual_seed(2)
+    y = torch.randn(3, 80, 32, generator=gen)
+    m = model(0, True, "bf16")
+    v = m.estimator(x.cuda(), y.cuda(), cond.cuda(), torch.tensor([0.2, 0.2, 0.2]), L)
+    torch.cuda.synchronize()
+    assert torch.isfinite(v).all()
+    assert float(v[0].abs().sum()) == 0.0 and float(v[1, :, 1:].abs().sum()) == 0.0
+    with pytest.raises(ValueError):
+        m.estimator(x.cuda(), y.cuda(), cond.cuda(), torch.tensor([0.2, 0.2, 0.2]), torch.tensor([0, 1, 33]))

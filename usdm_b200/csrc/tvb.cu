@@ -115,6 +115,10 @@ struct tvb_handle {
     size_t ws_bytes = 0;        // workspace
     int opt_attn_tc = 1;        // bf16 path: 1 = tcgen05 attention, 0 = CUDA-core attention (ablation / cross-check)
     int opt_conv_tc = 1;        // bf16 path: 1 = tcgen05 positional conv, 0 = CUDA-core conv
+    int profile = 0;            // 1: bracket every kernel with CUDA events on the launching stream (bench.py roofline leg)
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    std::vector<int> ev_cat;
     std::vector<void*> owned;                    // weight-side allocations
     std::map<std::string, RawTensor> raw;
 
@@ -146,6 +150,29 @@ struct tvb_handle {
     float *xpre = nullptr, *hres = nullptr, *vbuf = nullptr;
     float *z_work = nullptr, *z_hat = nullptr, *v_pred = nullptr;
     CUtensorMap tm_qkv_attn;                     // [Mp, 3H] box 128 x 64 (same as qkv.tm) kept for clarity
+};
+
+// per-kernel timing scopes (only active when option "profile" is set)
+enum ProfCat { PC_GEMM = 0, PC_ATTN = 1, PC_CONV = 2, PC_NORM = 3, PC_FRAME = 4, PC_OUT = 5, PC_NCAT = 8 };
+struct ProfScope {
+    tvb_handle* h;
+    cudaStream_t st;
+    bool on;
+    ProfScope(tvb_handle* h_, cudaStream_t st_, int cat) : h(h_), st(st_), on(h_ && h_->profile) {
+        if (!on) return;
+        while (h->ev_pool.size() < h->ev_used + 2) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            h->ev_pool.push_back(e);
+        }
+        h->ev_cat.push_back(cat);
+        cudaEventRecord(h->ev_pool[h->ev_used], st);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(h->ev_pool[h->ev_used + 1], st);
+        h->ev_used += 2;
+    }
 };
 
 static int dev_alloc(tvb_handle* h, std::vector<void*>& bag, void** p, size_t bytes) {
@@ -217,6 +244,7 @@ extern "C" int tvb_destroy(tvb_handle* h) {
     cudaDeviceSynchronize();
     for (void* p : h->owned) cudaFree(p);
     for (void* p : h->ws_owned) cudaFree(p);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
     return TVB_OK;
 }
@@ -271,6 +299,7 @@ static int make_lin(tvb_handle* h, Lin* lin, const float* w32, const float* bias
 template <int EPI>
 static int launch_sgemm(tvb_handle* h, const SgemmParams& p, cudaStream_t st) {
     dim3 grid((p.N + 127) / 128, (p.M + 127) / 128);
+    ProfScope ps(h, st, h->precision == TVB_PRECISION_BF16 ? PC_OUT : PC_GEMM);
     k_sgemm<EPI><<<grid, 256, 0, st>>>(p);
     h->launches++;
     CKL();
@@ -415,6 +444,22 @@ extern "C" int tvb_finalize_weights(tvb_handle* h) {
     return TVB_OK;
 }
 
+extern "C" int tvb_profile_read(tvb_handle* h, double* ms_by_cat, int64_t* launches_by_cat) {
+    if (!h || !ms_by_cat || !launches_by_cat) return fail(TVB_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    for (int i = 0; i < PC_NCAT; ++i) { ms_by_cat[i] = 0.0; launches_by_cat[i] = 0; }
+    for (size_t i = 0; i < h->ev_cat.size(); ++i) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]));
+        ms_by_cat[h->ev_cat[i]] += ms;
+        launches_by_cat[h->ev_cat[i]] += 1;
+    }
+    h->ev_used = 0;
+    h->ev_cat.clear();
+    return TVB_OK;
+}
+
 extern "C" int tvb_set_precision(tvb_handle* h, int32_t precision) {
     if (!h) return fail(TVB_ERR_INVALID, "null handle");
     if (precision != TVB_PRECISION_BF16 && precision != TVB_PRECISION_FP32_VALIDATE) return fail(TVB_ERR_INVALID, "unknown precision %d", precision);
@@ -428,6 +473,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     if (!h || !name) return fail(TVB_ERR_INVALID, "null argument");
     if (!strcmp(name, "attn_tc")) h->opt_attn_tc = value ? 1 : 0;
     else if (!strcmp(name, "conv_tc")) h->opt_conv_tc = value ? 1 : 0;
+    else if (!strcmp(name, "profile")) { h->profile = value ? 1 : 0; h->ev_used = 0; h->ev_cat.clear(); }
     else return fail(TVB_ERR_INVALID, "unknown option %s", name);
     return TVB_OK;
 }
@@ -568,7 +614,6 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
 // ----------------------------------------------------------------------------------------------------------------
 // kernel launch helpers
 // ----------------------------------------------------------------------------------------------------------------
-static bool g_gemm_attr_set = false;
 template <int EPI>
 static int launch_gemm_tc_t(tvb_handle* h, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const GemmParams& p,
                             cudaStream_t st, int num_sms) {
@@ -579,6 +624,7 @@ static int launch_gemm_tc_t(tvb_handle* h, const CUtensorMap& tmA, const CUtenso
     }
     const int tiles = (p.M / GEMM_BM) * (p.N / GEMM_BN);
     const int grid = tiles < num_sms ? tiles : num_sms;
+    ProfScope ps(h, st, PC_GEMM);
     gemm_tc_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(tmA, tmA2, tmB, p);
     if (h) h->launches++;
     CKL();
@@ -626,6 +672,7 @@ static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, Li
 
 static int layernorm(tvb_handle* h, const float* x, float* y, Act* yb, const float* g, const float* b, cudaStream_t st) {
     const int Mp = h->L.Mp, H = h->cfg.hidden_size;
+    ProfScope ps(h, st, PC_NORM);
     if (h->precision == TVB_PRECISION_BF16)
         k_layernorm<bf16><<<(Mp + 7) / 8, 256, 0, st>>>(x, y, yb ? yb->b16 : nullptr, g, b, h->L.row_seq, Mp, H, 1e-5f);
     else
@@ -637,6 +684,7 @@ static int layernorm(tvb_handle* h, const float* x, float* y, Act* yb, const flo
 
 static int attention(tvb_handle* h, cudaStream_t st) {
     const int H = h->cfg.hidden_size, nh = h->cfg.num_attention_heads;
+    ProfScope ps(h, st, PC_ATTN);
     if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc) {
         CK(launch_attn_tc_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, st));
     } else if (h->precision == TVB_PRECISION_BF16) {
@@ -656,6 +704,7 @@ static int posconv(tvb_handle* h, int i, bool last, cudaStream_t st) {
     const int Mp = h->L.Mp, H = c.hidden_size, taps = c.convpos_width;
     const bool bf = h->precision == TVB_PRECISION_BF16;
     const bool first = (i == 0);
+    ProfScope ps(h, st, PC_CONV);
     if (bf && h->opt_conv_tc) {
         // in: hin (first) or p1; out: p1 bf16 (not last) or xpre fp32 = gelu*mask + hin (last)
         const CUtensorMap& tin = first ? h->hin.tm : h->p1.tm;
@@ -692,6 +741,7 @@ static int posconv(tvb_handle* h, int i, bool last, cudaStream_t st) {
 static int prep_base(tvb_handle* h, const int64_t* x, const float* cond, int cond_is_zero, cudaStream_t st) {
     const tvb_config& c = h->cfg;
     const size_t smem = static_cast<size_t>(c.n_feats) * FP_ROWS * sizeof(float);
+    ProfScope ps(h, st, PC_FRAME);
     k_frame_proj<true><<<h->L.Mp / FP_ROWS, 256, smem, st>>>(h->L, h->plan_T, c.n_feats, c.hidden_size, h->Wc_t, cond, x, h->G, h->b_in,
                                                              c.n_tokens, cond_is_zero, nullptr, nullptr, 0.f, nullptr, h->base, nullptr);
     h->launches++;
@@ -704,8 +754,11 @@ static int run_estimator(tvb_handle* h, const float* y, const float* t_seq_dev, 
     const int Mp = h->L.Mp, H = c.hidden_size, nl = c.num_hidden_layers, nf = c.n_feats;
     const bool bf = h->precision == TVB_PRECISION_BF16;
     const size_t smem = static_cast<size_t>(nf) * FP_ROWS * sizeof(float);
-    k_frame_proj<false><<<Mp / FP_ROWS, 256, smem, st>>>(h->L, h->plan_T, nf, H, h->Wy_t, y, nullptr, nullptr, nullptr, 0, 0, h->base,
-                                                         t_seq_dev, t_uniform, h->freqs, h->hin.f32, bf ? h->hin.b16 : nullptr);
+    {
+        ProfScope ps(h, st, PC_FRAME);
+        k_frame_proj<false><<<Mp / FP_ROWS, 256, smem, st>>>(h->L, h->plan_T, nf, H, h->Wy_t, y, nullptr, nullptr, nullptr, 0, 0, h->base,
+                                                             t_seq_dev, t_uniform, h->freqs, h->hin.f32, bf ? h->hin.b16 : nullptr);
+    }
     h->launches++;
     CKL();
     for (int i = 0; i < c.convpos_depth; ++i) TRY(posconv(h, i, i == c.convpos_depth - 1, st));
@@ -761,6 +814,7 @@ extern "C" int tvb_estimator_forward(tvb_handle* h, const int64_t* x_dev, const 
 
 static int ode_update(tvb_handle* h, const OdeParams& p, cudaStream_t st) {
     const size_t n = static_cast<size_t>(p.B) * p.nf * p.T;
+    ProfScope ps(h, st, PC_OUT);
     k_ode_update<<<grid_for(n), 256, 0, st>>>(h->vbuf, h->cfg.n_feats, h->L, p);
     h->launches++;
     CKL();

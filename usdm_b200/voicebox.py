@@ -306,5 +306,16 @@ class Voicebox(nn.Module, PyTorchModelHubMixin):
     def kernel_launches(self) -> int:
         return 0 if self._handle is None else int(E.load_library().tvb_kernel_launches(self._handle))
 
+    PROFILE_CATEGORIES = ("gemm", "attention", "posconv", "layernorm", "frame_proj", "output")
+
+    def read_profile(self):
+        """{category: (milliseconds, launches)} accumulated since set_option("profile", 1) / the last read."""
+        if self._handle is None:
+            return {}
+        ms = (C.c_double * 8)()
+        n = (C.c_int64 * 8)()
+        E.check(E.load_library().tvb_profile_read(self._handle, ms, n))
+        return {name: (ms[i], int(n[i])) for i, name in enumerate(self.PROFILE_CATEGORIES)}
+
     def device_bytes(self) -> int:
         return 0 if self._handle is None else int(E.load_library().tvb_device_bytes(self._handle))
