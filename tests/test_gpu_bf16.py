@@ -16,15 +16,16 @@ def _est(m, g):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("attn_tc,conv_tc", [(0, 0), (1, 0), (0, 1), (1, 1)])
-def test_estimator_ragged_vs_reference_golden(attn_tc, conv_tc):
+@pytest.mark.parametrize("attn_tc,conv_tc,gemm_2cta", [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 1)])
+def test_estimator_ragged_vs_reference_golden(attn_tc, conv_tc, gemm_2cta):
     g = golden("estimator_ragged.pt")
     m = model(0, True, "bf16")
     m.set_option("attn_tc", attn_tc)
     m.set_option("conv_tc", conv_tc)
+    m.set_option("gemm_2cta", gemm_2cta)
     v = _est(m, g)
     err = rel_l2(v, g["v"])
-    print(f"bf16 estimator (attn_tc={attn_tc}, conv_tc={conv_tc}) rel-L2 vs reference fp32: {err:.3e}")
+    print(f"bf16 estimator (attn_tc={attn_tc}, conv_tc={conv_tc}, gemm_2cta={gemm_2cta}) rel-L2 vs reference fp32: {err:.3e}")
     assert torch.isfinite(v).all()
     assert err < TOL
     for b, L in enumerate(g["lengths"].tolist()):

@@ -27,6 +27,16 @@ def _run(M, N, K, epi, seed=0):
 
 
 @pytest.mark.timeout(300)
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (256, 512, 128), (512, 256, 512), (1024, 1024, 1024),
+                                   (768, 3072, 1024), (256, 1024, 4096), (148 * 128 * 2 + 256, 1024, 1024)])
+def test_gemm_pair_f32_epilogue(M, N, K):
+    """CTA-pair (cta_group::2, M=256) kernel."""
+    ref, _, of, _ = _run(M, N, K, 4 | 0x100)
+    err = (of - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
+@pytest.mark.timeout(300)
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (128, 256, 512), (1024, 1024, 1024),
                                    (384, 3072, 1024), (256, 1024, 4096), (148 * 128 * 2 + 128, 1024, 1024)])
 def test_gemm_f32_epilogue(M, N, K):
@@ -36,10 +46,11 @@ def test_gemm_f32_epilogue(M, N, K):
 
 
 @pytest.mark.timeout(300)
+@pytest.mark.parametrize("pair", [0, 0x100])
 @pytest.mark.parametrize("epi", [0, 1, 2, 3])
-def test_gemm_epilogues(epi):
+def test_gemm_epilogues(epi, pair):
     M, N, K = 512, 1024, 1024
-    ref, resid, of, ob = _run(M, N, K, epi, seed=epi + 1)
+    ref, resid, of, ob = _run(M, N, K, epi | pair, seed=epi + 1)
     if epi == 0:
         want = ref.to(torch.bfloat16).float(); got = ob.float()
     elif epi == 1:

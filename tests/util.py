@@ -40,6 +40,7 @@ def model(seed=0, perturb=False, precision="bf16"):
     m.set_precision(precision)
     m.set_option("attn_tc", 1)
     m.set_option("conv_tc", 1)
+    m.set_option("gemm_2cta", 1)
     return m
 
 

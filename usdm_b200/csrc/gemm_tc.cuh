@@ -201,4 +201,179 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+
+// ================================================================================================================
+// CTA-pair version (default): a cluster of 2 CTAs on adjacent SMs computes one 256 x 256 output tile with
+// tcgen05.mma.cta_group::2 (M = 256).  Each CTA stages its own 128 rows of A and HALF (128 rows) of the W tile, so a
+// k-block costs 32 KB of L2->smem traffic per CTA instead of 48 KB and the smem read traffic of the MMA halves: the
+// single-CTA kernel above is L2/smem-bandwidth bound near 0.9 PFLOP/s at K = 1024 (measured, profiles/r01).
+//   warp 0 TMA producer (both CTAs; completion bytes credited to the leader's barrier), warp 1 MMA issuer (leader CTA
+//   only; commits multicast to both CTAs), warps 2..9 epilogue (8 warps: TMEM lane quadrant x column half), each CTA
+//   draining its own 128 x 256 fp32 accumulator.  6-stage ring, 2 accumulator stages.
+// ================================================================================================================
+constexpr int G2_STAGES = 6;
+constexpr int G2_A_BYTES = 128 * GEMM_BK * 2;                // 16 KB (this CTA's 128 rows of A)
+constexpr int G2_B_BYTES = 128 * GEMM_BK * 2;                // 16 KB (this CTA's half of the 256 W rows)
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 1024 + 256;
+constexpr int G2_THREADS = 320;
+constexpr int G2_EPI_WARPS = 8;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // identical carve-up in both CTAs (the dynamic smem base offset is the same for every CTA of a kernel)
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + G2_STAGES;
+    uint64_t* tfull_bar = empty_bar + G2_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta = cluster_ctarank();          // 0 = leader
+    const int tiles_n = p.N / 256;
+    const int num_tiles = (p.M / 256) * tiles_n;
+    const int num_kb = p.K / GEMM_BK;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    if (warp_idx == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB); }
+    if (warp_idx == 1 && lane == 0) {
+        for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * G2_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp_idx == 2) tmem_alloc_2cta<512>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp_idx == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int m0 = (tile / tiles_n) * 256 + static_cast<int>(cta) * 128;
+                const int n0 = (tile % tiles_n) * 256 + static_cast<int>(cta) * 128;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * G2_STAGE_BYTES;
+                    if (cta == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);   // bytes of BOTH CTAs
+                    const int k0 = kb * GEMM_BK;
+                    if (k0 < p.K1) tma_load_2d_2cta(sa, &tmA, &full_bar[stage], k0, m0);
+                    else           tma_load_2d_2cta(sa, &tmA2, &full_bar[stage], k0 - p.K1, m0);
+                    tma_load_2d_2cta(sa + G2_A_BYTES, &tmB, &full_bar[stage], k0, n0);
+                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        if (cta == 0 && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(256, 256);
+            int stage = 0; uint32_t phase = 0; int it = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+                const int as = it & 1;
+                mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 256;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
+                    const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+                    const uint64_t db = make_smem_desc_sw128(sa + G2_A_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k) umma_ss_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit_2cta(&empty_bar[stage], 3);
+                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2cta(&tfull_bar[as], 3);
+            }
+        }
+    } else {
+        const int quad = warp_idx & 3;
+        const int chalf = (warp_idx - 2) >> 2;               // which 128 of the 256 accumulator columns
+        int it = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+            const int as = it & 1;
+            const int m0 = (tile / tiles_n) * 256 + static_cast<int>(cta) * 128;
+            const int n0 = (tile % tiles_n) * 256 + chalf * 128;
+            const int row = m0 + quad * 32 + lane;
+            const size_t row_off = static_cast<size_t>(row) * p.ld_out;
+            float4 rs[8];
+            if constexpr (EPI == EPI_RESID_F32) {            // residual does not depend on the accumulator: fetch early
+                const float4* r4 = reinterpret_cast<const float4*>(p.resid + row_off + n0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rs[j] = r4[j];
+            }
+            mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256 + chalf * 128 + c * 32, r);
+                float4 rn[8];
+                if constexpr (EPI == EPI_RESID_F32) {
+                    if (c + 1 < 4) {
+                        const float4* r4 = reinterpret_cast<const float4*>(p.resid + row_off + n0 + (c + 1) * 32);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) rn[j] = r4[j];
+                    }
+                }
+                tmem_ld_wait();
+                const int col = n0 + c * 32;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.bias != nullptr) {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = __ldg(b4 + j);
+                        v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                    }
+                }
+                if constexpr (EPI == EPI_GELU_BF16) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                }
+                if constexpr (EPI == EPI_RESID_F32) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        v[4 * j + 0] += rs[j].x; v[4 * j + 1] += rs[j].y; v[4 * j + 2] += rs[j].z; v[4 * j + 3] += rs[j].w;
+                    }
+                    if (c + 1 < 4) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) rs[j] = rn[j];
+                    }
+                }
+                if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_DUAL || EPI == EPI_F32) {
+                    float4* o4 = reinterpret_cast<float4*>(p.out_f32 + row_off + col);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                if constexpr (EPI == EPI_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_DUAL) {
+                    uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + row_off + col);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);   // the leader's MMA thread owns accumulator reuse
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                                               // nobody exits while the peer may still signal it
+    if (warp_idx == 2) {
+        tc_fence_after();
+        tmem_dealloc_2cta<512>(tmem_base);
+    }
+}
+
 }  // namespace tvb

@@ -91,7 +91,8 @@ struct Lin {                 // one nn.Linear: y = x W^T + b
     bf16* w16 = nullptr;
     const float* bias = nullptr;
     int N = 0, K = 0;
-    CUtensorMap tm;          // B operand map: [N, K], box 256 x 64
+    CUtensorMap tm;          // B operand map: [N, K], box 256 x 64 (single-CTA kernel)
+    CUtensorMap tm2;         // B operand map: [N, K], box 128 x 64 (CTA-pair kernel: each CTA stages half of the W tile)
 };
 struct Act {                 // an activation buffer [Mp, C] in the precision of the active path
     float* f32 = nullptr;
@@ -115,6 +116,7 @@ struct tvb_handle {
     size_t ws_bytes = 0;        // workspace
     int opt_attn_tc = 1;        // bf16 path: 1 = tcgen05 attention, 0 = CUDA-core attention (ablation / cross-check)
     int opt_conv_tc = 1;        // bf16 path: 1 = tcgen05 positional conv, 0 = CUDA-core conv
+    int opt_gemm_2cta = 1;      // bf16 path: 1 = CTA-pair (cta_group::2) GEMM, 0 = single-CTA GEMM
     int profile = 0;            // 1: bracket every kernel with CUDA events on the launching stream (bench.py roofline leg)
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -293,6 +295,7 @@ static int make_lin(tvb_handle* h, Lin* lin, const float* w32, const float* bias
     k_f32_to_bf16<<<grid_for(static_cast<size_t>(N) * K), 256>>>(w32, lin->w16, static_cast<size_t>(N) * K);
     CKL();
     TRY(make_tmap(&lin->tm, lin->w16, N, K, K, GEMM_BN));
+    TRY(make_tmap(&lin->tm2, lin->w16, N, K, K, 128));
     return TVB_OK;
 }
 
@@ -473,6 +476,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     if (!h || !name) return fail(TVB_ERR_INVALID, "null argument");
     if (!strcmp(name, "attn_tc")) h->opt_attn_tc = value ? 1 : 0;
     else if (!strcmp(name, "conv_tc")) h->opt_conv_tc = value ? 1 : 0;
+    else if (!strcmp(name, "gemm_2cta")) h->opt_gemm_2cta = value ? 1 : 0;
     else if (!strcmp(name, "profile")) { h->profile = value ? 1 : 0; h->ev_used = 0; h->ev_cat.clear(); }
     else return fail(TVB_ERR_INVALID, "unknown option %s", name);
     return TVB_OK;
@@ -514,8 +518,9 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
         o += lengths[b] + 1 + GAP;
     }
     if (o > (1ll << 30)) return fail(TVB_ERR_INVALID, "batch too large");
-    const int half = static_cast<int>((o + 127) / 128 * 128);
     const int nhalf = cfg_double ? 2 : 1;
+    const int64_t halign = cfg_double ? 128 : 256;          // Mp must be a multiple of 256 (CTA-pair GEMM tiles)
+    const int half = static_cast<int>((o + halign - 1) / halign * halign);
     const int Mp = half * nhalf;
     const int nseq = B * nhalf;
     std::vector<int> row_seq(Mp, -1), row_pos(Mp, 0), seqinfo(4 * static_cast<size_t>(nseq));
@@ -643,6 +648,36 @@ static int launch_gemm_tc(tvb_handle* h, int epi, const CUtensorMap& tmA, const 
     return fail(TVB_ERR_INVALID, "unknown epilogue %d", epi);
 }
 
+template <int EPI>
+static int launch_gemm2_tc_t(tvb_handle* h, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const GemmParams& p,
+                             cudaStream_t st, int num_sms) {
+    static bool attr = false;
+    if (!attr) {
+        CK(cudaFuncSetAttribute(gemm2_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+        attr = true;
+    }
+    const int tiles = (p.M / 256) * (p.N / 256);
+    int grid = 2 * tiles < (num_sms & ~1) ? 2 * tiles : (num_sms & ~1);
+    ProfScope ps(h, st, PC_GEMM);
+    gemm2_tc_kernel<EPI><<<grid, G2_THREADS, G2_SMEM_BYTES, st>>>(tmA, tmA2, tmB, p);
+    if (h) h->launches++;
+    CKL();
+    return TVB_OK;
+}
+// CTA-pair GEMM; tmB must be the box-128 weight map.
+static int launch_gemm2_tc(tvb_handle* h, int epi, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
+                           const GemmParams& p, cudaStream_t st, int num_sms) {
+    if (p.M % 256 || p.N % 256 || p.K % GEMM_BK || p.K1 % GEMM_BK) return fail(TVB_ERR_INVALID, "gemm shape %dx%dx%d not tileable by CTA pairs", p.M, p.N, p.K);
+    switch (epi) {
+        case EPI_BF16: return launch_gemm2_tc_t<EPI_BF16>(h, tmA, tmA2, tmB, p, st, num_sms);
+        case EPI_GELU_BF16: return launch_gemm2_tc_t<EPI_GELU_BF16>(h, tmA, tmA2, tmB, p, st, num_sms);
+        case EPI_RESID_F32: return launch_gemm2_tc_t<EPI_RESID_F32>(h, tmA, tmA2, tmB, p, st, num_sms);
+        case EPI_DUAL: return launch_gemm2_tc_t<EPI_DUAL>(h, tmA, tmA2, tmB, p, st, num_sms);
+        case EPI_F32: return launch_gemm2_tc_t<EPI_F32>(h, tmA, tmA2, tmB, p, st, num_sms);
+    }
+    return fail(TVB_ERR_INVALID, "unknown epilogue %d", epi);
+}
+
 enum LinEpi { LE_PLAIN, LE_GELU, LE_RESID, LE_DUAL };
 // y = [a | a2] W^T + b with the epilogue the call site needs, in the active precision.
 //   LE_PLAIN: -> out (Act)          LE_GELU: -> gelu -> out (Act)
@@ -655,6 +690,7 @@ static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, Li
         p.M = Mp; p.N = lin.N; p.K = lin.K; p.K1 = a2 ? a.C : lin.K;
         p.bias = lin.bias; p.resid = resid; p.out_f32 = out_f32; p.out_bf16 = out ? out->b16 : nullptr; p.ld_out = lin.N;
         const int e = epi == LE_PLAIN ? EPI_BF16 : epi == LE_GELU ? EPI_GELU_BF16 : epi == LE_RESID ? EPI_RESID_F32 : EPI_DUAL;
+        if (h->opt_gemm_2cta) return launch_gemm2_tc(h, e, a.tm, a2 ? a2->tm : a.tm, lin.tm2, p, st, h->num_sms);
         return launch_gemm_tc(h, e, a.tm, a2 ? a2->tm : a.tm, lin.tm, p, st, h->num_sms);
     }
     SgemmParams p{};
@@ -902,11 +938,13 @@ extern "C" int tvb_debug_gemm_bf16(int device, const void* a_dev, const void* w_
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(TVB_ERR_INVALID, "sm_100a device required");
+    const bool pair = (epilogue & 0x100) != 0;
     CUtensorMap tmA, tmB;
     TRY(make_tmap(&tmA, a_dev, M, K, K, 128));
-    TRY(make_tmap(&tmB, w_dev, N, K, K, GEMM_BN));
+    TRY(make_tmap(&tmB, w_dev, N, K, K, pair ? 128 : GEMM_BN));
     GemmParams p{};
     p.M = M; p.N = N; p.K = K; p.K1 = K; p.bias = bias_dev; p.resid = resid_dev; p.out_f32 = out_f32_dev;
     p.out_bf16 = static_cast<bf16*>(out_bf16_dev); p.ld_out = N;
+    if (pair) return launch_gemm2_tc(nullptr, epilogue & 0xff, tmA, tmA, tmB, p, static_cast<cudaStream_t>(stream), prop.multiProcessorCount);
     return launch_gemm_tc(nullptr, epilogue, tmA, tmA, tmB, p, static_cast<cudaStream_t>(stream), prop.multiProcessorCount);
 }
