@@ -205,32 +205,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ================================================================================================================
 // CTA-pair version (default): a cluster of 2 CTAs on adjacent SMs computes one 256 x 256 output tile with
 // tcgen05.mma.cta_group::2 (M = 256).  Each CTA stages its own 128 rows of A and HALF (128 rows) of the W tile, so a
-// k-block costs 32 KB of L2->smem traffic per CTA instead of 48 KB and the smem read traffic of the MMA halves: the
-// single-CTA kernel above is L2/smem-bandwidth bound near 0.9 PFLOP/s at K = 1024 (measured, profiles/r01).
+// k-block costs 32 KB of L2->smem traffic per CTA instead of 48 KB and the smem read traffic of the MMA halves.
 //   warp 0 TMA producer (both CTAs; completion bytes credited to the leader's barrier), warp 1 MMA issuer (leader CTA
 //   only; commits multicast to both CTAs), warps 2..9 epilogue (8 warps: TMEM lane quadrant x column half), each CTA
-//   draining its own 128 x 256 fp32 accumulator.  6-stage ring, 2 accumulator stages.
+//   draining its own 128 x 256 fp32 accumulator.  4-stage operand ring, 2 accumulator stages.
+// Epilogue data path (measured: per-row direct global accesses made the K=1024 GEMMs epilogue-bound at 30-65 % tensor
+// activity, profiles/r01): every warp owns two 4 KB smem staging tiles (32 rows x 128 B, 128-B swizzle).  The residual
+// tile is TMA-loaded into the staging tile ahead of time, the thread that owns a TMEM lane adds bias/residual (or GELU)
+// to its row in place, and one elected lane TMA-stores the tile: all global traffic is coalesced by the TMA engine.
 // ================================================================================================================
-constexpr int G2_STAGES = 6;
+constexpr int G2_STAGES = 4;
 constexpr int G2_A_BYTES = 128 * GEMM_BK * 2;                // 16 KB (this CTA's 128 rows of A)
 constexpr int G2_B_BYTES = 128 * GEMM_BK * 2;                // 16 KB (this CTA's half of the 256 W rows)
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
-constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 1024 + 256;
-constexpr int G2_THREADS = 320;
 constexpr int G2_EPI_WARPS = 8;
+constexpr int G2_EPI_TILE = 4096;                            // 32 rows x 128 B
+constexpr int G2_SMEM_EPI = G2_STAGES * G2_STAGE_BYTES;
+constexpr int G2_SMEM_BAR = G2_SMEM_EPI + G2_EPI_WARPS * 2 * G2_EPI_TILE;
+constexpr int G2_SMEM_BYTES = G2_SMEM_BAR + 1024 + 512;
+constexpr int G2_THREADS = 320;
+
+struct Gemm2Maps {
+    CUtensorMap a, a2, b;     // operands
+    CUtensorMap out;          // fp32 [M,N] box 32x32 (EPI_RESID_F32 / EPI_DUAL / EPI_F32) or bf16 [M,N] box 64x32 (EPI_BF16 / EPI_GELU_BF16)
+    CUtensorMap resid;        // fp32 [M,N] box 32x32 (EPI_RESID_F32)
+};
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
-gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm2_tc_kernel(const __grid_constant__ Gemm2Maps tm, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     // identical carve-up in both CTAs (the dynamic smem base offset is the same for every CTA of a kernel)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_SMEM_BAR);
     uint64_t* empty_bar = full_bar + G2_STAGES;
     uint64_t* tfull_bar = empty_bar + G2_STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* rbar = tempty_bar + 2;                  // [8 warps][2 buffers] residual-tile arrival
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 2 * G2_EPI_WARPS);
 
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta = cluster_ctarank();          // 0 = leader
@@ -239,10 +251,14 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int num_kb = p.K / GEMM_BK;
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
-    if (warp_idx == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB); }
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tm.a); tma_prefetch_desc(&tm.a2); tma_prefetch_desc(&tm.b); tma_prefetch_desc(&tm.out);
+        if (EPI == EPI_RESID_F32) tma_prefetch_desc(&tm.resid);
+    }
     if (warp_idx == 1 && lane == 0) {
         for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * G2_EPI_WARPS); }
+        for (int s = 0; s < 2 * G2_EPI_WARPS; ++s) mbar_init(&rbar[s], 1);
         fence_barrier_init();
     }
     if (warp_idx == 2) tmem_alloc_2cta<512>(tmem_slot);
@@ -262,9 +278,9 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     uint8_t* sa = smem + stage * G2_STAGE_BYTES;
                     if (cta == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);   // bytes of BOTH CTAs
                     const int k0 = kb * GEMM_BK;
-                    if (k0 < p.K1) tma_load_2d_2cta(sa, &tmA, &full_bar[stage], k0, m0);
-                    else           tma_load_2d_2cta(sa, &tmA2, &full_bar[stage], k0 - p.K1, m0);
-                    tma_load_2d_2cta(sa + G2_A_BYTES, &tmB, &full_bar[stage], k0, n0);
+                    if (k0 < p.K1) tma_load_2d_2cta(sa, &tm.a, &full_bar[stage], k0, m0);
+                    else           tma_load_2d_2cta(sa, &tm.a2, &full_bar[stage], k0 - p.K1, m0);
+                    tma_load_2d_2cta(sa + G2_A_BYTES, &tm.b, &full_bar[stage], k0, n0);
                     if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -293,79 +309,118 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
     } else {
+        // ------------------------------------------ epilogue ------------------------------------------
+        constexpr bool kBf16Out = (EPI == EPI_BF16 || EPI == EPI_GELU_BF16);
+        constexpr int kChunkCols = kBf16Out ? 64 : 32;            // one staging tile row = 128 B
+        constexpr int kChunks = 128 / kChunkCols;                 // per warp per tile
+        const int ew = warp_idx - 2;
         const int quad = warp_idx & 3;
-        const int chalf = (warp_idx - 2) >> 2;               // which 128 of the 256 accumulator columns
+        const int chalf = ew >> 2;                                // which 128 of the 256 accumulator columns
+        uint8_t* stg = smem + G2_SMEM_EPI + ew * 2 * G2_EPI_TILE;
+        uint64_t* rb = rbar + ew * 2;
+        const int r7 = lane & 7;
+        uint32_t kc = 0;                                          // running chunk counter -> staging buffer / parity
+        auto chunk_coords = [&](int tile, int c, int& col, int& row) {
+            row = (tile / tiles_n) * 256 + static_cast<int>(cta) * 128 + quad * 32;
+            col = (tile % tiles_n) * 256 + chalf * 128 + c * kChunkCols;
+        };
+        if constexpr (EPI == EPI_RESID_F32) {
+            if (lane == 0 && cluster_id < num_tiles) {
+                int col, row;
+                chunk_coords(cluster_id, 0, col, row);
+                mbar_arrive_expect_tx(&rb[0], G2_EPI_TILE);
+                tma_load_2d(stg, &tm.resid, &rb[0], col, row);
+            }
+        }
         int it = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
             const int as = it & 1;
-            const int m0 = (tile / tiles_n) * 256 + static_cast<int>(cta) * 128;
-            const int n0 = (tile % tiles_n) * 256 + chalf * 128;
-            const int row = m0 + quad * 32 + lane;
-            const size_t row_off = static_cast<size_t>(row) * p.ld_out;
-            float4 rs[8];
-            if constexpr (EPI == EPI_RESID_F32) {            // residual does not depend on the accumulator: fetch early
-                const float4* r4 = reinterpret_cast<const float4*>(p.resid + row_off + n0);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) rs[j] = r4[j];
-            }
             mbar_wait(&tfull_bar[as], (it >> 1) & 1);
             tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256 + chalf * 128 + c * 32, r);
-                float4 rn[8];
-                if constexpr (EPI == EPI_RESID_F32) {
-                    if (c + 1 < 4) {
-                        const float4* r4 = reinterpret_cast<const float4*>(p.resid + row_off + n0 + (c + 1) * 32);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) rn[j] = r4[j];
+            const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256 + chalf * 128;
+#pragma unroll 1
+            for (int c = 0; c < kChunks; ++c, ++kc) {
+                const int buf = kc & 1;
+                uint8_t* tile_s = stg + buf * G2_EPI_TILE;
+                int col, row;
+                chunk_coords(tile, c, col, row);
+                if (lane == 0) {
+                    if constexpr (EPI == EPI_RESID_F32) {
+                        // the other buffer's last store must have finished reading before the next residual lands in it
+                        tma_store_wait_read<0>();
+                        int nt = tile, nc = c + 1;
+                        if (nc == kChunks) { nc = 0; nt = tile + num_clusters; }
+                        if (nt < num_tiles) {
+                            int ncol, nrow;
+                            chunk_coords(nt, nc, ncol, nrow);
+                            mbar_arrive_expect_tx(&rb[buf ^ 1], G2_EPI_TILE);
+                            tma_load_2d(stg + (buf ^ 1) * G2_EPI_TILE, &tm.resid, &rb[buf ^ 1], ncol, nrow);
+                        }
+                    } else {
+                        tma_store_wait_read<1>();                 // the store issued two chunks ago (same buffer) is done reading
                     }
                 }
-                tmem_ld_wait();
-                const int col = n0 + c * 32;
-                float v[32];
+                __syncwarp();
+                float v[kChunkCols];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                for (int q = 0; q < kChunkCols / 32; ++q) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_acc + c * kChunkCols + q * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[q * 32 + j] = __uint_as_float(r[j]);
+                }
                 if (p.bias != nullptr) {
                     const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < kChunkCols / 4; ++j) {
                         const float4 b = __ldg(b4 + j);
                         v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
                     }
                 }
                 if constexpr (EPI == EPI_GELU_BF16) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                    for (int j = 0; j < kChunkCols; ++j) v[j] = gelu_erf_fast(v[j]);
                 }
+                uint8_t* rowp = tile_s + lane * 128;               // this thread's row of the staging tile
                 if constexpr (EPI == EPI_RESID_F32) {
+                    mbar_wait(&rb[buf], (kc >> 1) & 1);            // residual tile landed (async proxy -> visible after wait)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        v[4 * j + 0] += rs[j].x; v[4 * j + 1] += rs[j].y; v[4 * j + 2] += rs[j].z; v[4 * j + 3] += rs[j].w;
+                        float4* q4 = reinterpret_cast<float4*>(rowp + ((j ^ r7) << 4));
+                        const float4 rr = *q4;
+                        *q4 = make_float4(v[4 * j] + rr.x, v[4 * j + 1] + rr.y, v[4 * j + 2] + rr.z, v[4 * j + 3] + rr.w);
                     }
-                    if (c + 1 < 4) {
+                } else if constexpr (kBf16Out) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) rs[j] = rn[j];
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(rowp + ((j ^ r7) << 4)) =
+                            make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                       pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(rowp + ((j ^ r7) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    if constexpr (EPI == EPI_DUAL) {               // bf16 copy for the next GEMM (12 launches / pass): direct stores
+                        uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(row + lane) * p.ld_out + col);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
                     }
                 }
-                if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_DUAL || EPI == EPI_F32) {
-                    float4* o4 = reinterpret_cast<float4*>(p.out_f32 + row_off + col);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                }
-                if constexpr (EPI == EPI_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_DUAL) {
-                    uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + row_off + col);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tm.out, tile_s, col, row);
+                    tma_store_commit();
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);   // the leader's MMA thread owns accumulator reuse
         }
+        if (lane == 0) tma_store_wait_read<0>();
     }
 
     tc_fence_before();

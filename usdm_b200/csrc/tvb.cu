@@ -63,14 +63,17 @@ static int resolve_driver() {
     g_encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
     return TVB_OK;
 }
-// 2-D bf16 row-major [rows, cols] (leading dimension ld elements), box = box_rows x 64 columns, 128-byte swizzle.
-static int make_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols = 64) {
+// 2-D row-major [rows, cols] (leading dimension ld elements), box = box_rows x box_cols (128 bytes wide), 128-byte swizzle.
+// Default element type bf16 (box 64 columns); f32 = true makes an fp32 map (box 32 columns).
+static int make_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols = 64,
+                     bool f32 = false) {
     TRY(resolve_driver());
+    const int esz = f32 ? 4 : 2;
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * esz};
     cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(TVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
@@ -99,6 +102,7 @@ struct Act {                 // an activation buffer [Mp, C] in the precision of
     bf16* b16 = nullptr;
     int C = 0;
     CUtensorMap tm;          // A operand map (bf16 path): box 128 x 64
+    CUtensorMap tm_out;      // epilogue TMA-store map (bf16 path): box 32 rows x 64 columns
 };
 struct LayerW {
     Lin qkv, o, f1, f2;
@@ -144,14 +148,14 @@ struct tvb_handle {
     int *d_row_seq = nullptr, *d_row_pos = nullptr, *d_seq = nullptr;   // d_seq: 4 * nseq_cap ints
     int seq_cap = 0;
     int2* d_work16 = nullptr; int work16_cap = 0, n_work16 = 0;        // 16-query tiles (CUDA-core attention)
-    int4* d_work128 = nullptr; int work128_cap = 0, n_work128 = 0;     // 128-query tiles (tcgen05 attention)
+    int4* d_work128 = nullptr; int work128_cap = 0, n_work128 = 0;     // ATT_BQ-query tiles (tcgen05 attention)
     float* d_tseq = nullptr;
     int plan_B = 0, plan_T = 0, plan_cfg = 0, plan_half = 0;
     float* base = nullptr;
     Act hin, p1, slots[32], hbA, hbB, qkv, ctx, mid;
     float *xpre = nullptr, *hres = nullptr, *vbuf = nullptr;
     float *z_work = nullptr, *z_hat = nullptr, *v_pred = nullptr;
-    CUtensorMap tm_qkv_attn;                     // [Mp, 3H] box 128 x 64 (same as qkv.tm) kept for clarity
+    CUtensorMap tm_xpre, tm_hres;                // fp32 [Mp, H] epilogue maps (box 32 rows x 32 columns): TMA store / residual load
 };
 
 // per-kernel timing scopes (only active when option "profile" is set)
@@ -537,7 +541,7 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
         seqinfo[3 * nseq + s] = uncond;
         for (int i = 0; i < len; ++i) { row_seq[start + i] = s; row_pos[start + i] = i; }
         for (int q0 = 0; q0 < len; q0 += 16) work16.push_back(make_int2(s, q0));
-        for (int q0 = 0; q0 < len; q0 += 128) work128.push_back(make_int4(s, q0, start, len));
+        for (int q0 = 0; q0 < len; q0 += ATT_BQ) work128.push_back(make_int4(s, q0, start, len));
     }
     // ---- workspace (re)allocation
     const bool bf = h->precision == TVB_PRECISION_BF16;
@@ -612,6 +616,10 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
         TRY(make_tmap(&h->qkv.tm, h->qkv.b16, Mp, 3 * H, 3 * H, 128));
         TRY(make_tmap(&h->ctx.tm, h->ctx.b16, Mp, H, H, 128));
         TRY(make_tmap(&h->mid.tm, h->mid.b16, Mp, F, F, 128));
+        TRY(make_tmap(&h->qkv.tm_out, h->qkv.b16, Mp, 3 * H, 3 * H, 32));
+        TRY(make_tmap(&h->mid.tm_out, h->mid.b16, Mp, F, F, 32));
+        TRY(make_tmap(&h->tm_xpre, h->xpre, Mp, H, H, 32, 32, true));
+        TRY(make_tmap(&h->tm_hres, h->hres, Mp, H, H, 32, 32, true));
     }
     return TVB_OK;
 }
@@ -649,8 +657,7 @@ static int launch_gemm_tc(tvb_handle* h, int epi, const CUtensorMap& tmA, const 
 }
 
 template <int EPI>
-static int launch_gemm2_tc_t(tvb_handle* h, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const GemmParams& p,
-                             cudaStream_t st, int num_sms) {
+static int launch_gemm2_tc_t(tvb_handle* h, const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st, int num_sms) {
     static bool attr = false;
     if (!attr) {
         CK(cudaFuncSetAttribute(gemm2_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
@@ -659,21 +666,20 @@ static int launch_gemm2_tc_t(tvb_handle* h, const CUtensorMap& tmA, const CUtens
     const int tiles = (p.M / 256) * (p.N / 256);
     int grid = 2 * tiles < (num_sms & ~1) ? 2 * tiles : (num_sms & ~1);
     ProfScope ps(h, st, PC_GEMM);
-    gemm2_tc_kernel<EPI><<<grid, G2_THREADS, G2_SMEM_BYTES, st>>>(tmA, tmA2, tmB, p);
+    gemm2_tc_kernel<EPI><<<grid, G2_THREADS, G2_SMEM_BYTES, st>>>(maps, p);
     if (h) h->launches++;
     CKL();
     return TVB_OK;
 }
-// CTA-pair GEMM; tmB must be the box-128 weight map.
-static int launch_gemm2_tc(tvb_handle* h, int epi, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
-                           const GemmParams& p, cudaStream_t st, int num_sms) {
+// CTA-pair GEMM; maps.b must be the box-128 weight map, maps.out / maps.resid the epilogue maps of the destination.
+static int launch_gemm2_tc(tvb_handle* h, int epi, const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st, int num_sms) {
     if (p.M % 256 || p.N % 256 || p.K % GEMM_BK || p.K1 % GEMM_BK) return fail(TVB_ERR_INVALID, "gemm shape %dx%dx%d not tileable by CTA pairs", p.M, p.N, p.K);
     switch (epi) {
-        case EPI_BF16: return launch_gemm2_tc_t<EPI_BF16>(h, tmA, tmA2, tmB, p, st, num_sms);
-        case EPI_GELU_BF16: return launch_gemm2_tc_t<EPI_GELU_BF16>(h, tmA, tmA2, tmB, p, st, num_sms);
-        case EPI_RESID_F32: return launch_gemm2_tc_t<EPI_RESID_F32>(h, tmA, tmA2, tmB, p, st, num_sms);
-        case EPI_DUAL: return launch_gemm2_tc_t<EPI_DUAL>(h, tmA, tmA2, tmB, p, st, num_sms);
-        case EPI_F32: return launch_gemm2_tc_t<EPI_F32>(h, tmA, tmA2, tmB, p, st, num_sms);
+        case EPI_BF16: return launch_gemm2_tc_t<EPI_BF16>(h, maps, p, st, num_sms);
+        case EPI_GELU_BF16: return launch_gemm2_tc_t<EPI_GELU_BF16>(h, maps, p, st, num_sms);
+        case EPI_RESID_F32: return launch_gemm2_tc_t<EPI_RESID_F32>(h, maps, p, st, num_sms);
+        case EPI_DUAL: return launch_gemm2_tc_t<EPI_DUAL>(h, maps, p, st, num_sms);
+        case EPI_F32: return launch_gemm2_tc_t<EPI_F32>(h, maps, p, st, num_sms);
     }
     return fail(TVB_ERR_INVALID, "unknown epilogue %d", epi);
 }
@@ -690,7 +696,14 @@ static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, Li
         p.M = Mp; p.N = lin.N; p.K = lin.K; p.K1 = a2 ? a.C : lin.K;
         p.bias = lin.bias; p.resid = resid; p.out_f32 = out_f32; p.out_bf16 = out ? out->b16 : nullptr; p.ld_out = lin.N;
         const int e = epi == LE_PLAIN ? EPI_BF16 : epi == LE_GELU ? EPI_GELU_BF16 : epi == LE_RESID ? EPI_RESID_F32 : EPI_DUAL;
-        if (h->opt_gemm_2cta) return launch_gemm2_tc(h, e, a.tm, a2 ? a2->tm : a.tm, lin.tm2, p, st, h->num_sms);
+        if (h->opt_gemm_2cta) {
+            Gemm2Maps maps;
+            maps.a = a.tm; maps.a2 = a2 ? a2->tm : a.tm; maps.b = lin.tm2;
+            if (epi == LE_PLAIN || epi == LE_GELU) maps.out = out->tm_out;
+            else maps.out = (out_f32 == h->xpre) ? h->tm_xpre : h->tm_hres;
+            maps.resid = (resid == h->xpre) ? h->tm_xpre : h->tm_hres;
+            return launch_gemm2_tc(h, e, maps, p, st, h->num_sms);
+        }
         return launch_gemm_tc(h, e, a.tm, a2 ? a2->tm : a.tm, lin.tm, p, st, h->num_sms);
     }
     SgemmParams p{};
@@ -945,6 +958,15 @@ extern "C" int tvb_debug_gemm_bf16(int device, const void* a_dev, const void* w_
     GemmParams p{};
     p.M = M; p.N = N; p.K = K; p.K1 = K; p.bias = bias_dev; p.resid = resid_dev; p.out_f32 = out_f32_dev;
     p.out_bf16 = static_cast<bf16*>(out_bf16_dev); p.ld_out = N;
-    if (pair) return launch_gemm2_tc(nullptr, epilogue & 0xff, tmA, tmA, tmB, p, static_cast<cudaStream_t>(stream), prop.multiProcessorCount);
+    if (pair) {
+        const int e = epilogue & 0xff;
+        Gemm2Maps maps;
+        maps.a = tmA; maps.a2 = tmA; maps.b = tmB;
+        if (e == EPI_BF16 || e == EPI_GELU_BF16) TRY(make_tmap(&maps.out, out_bf16_dev, M, N, N, 32));
+        else TRY(make_tmap(&maps.out, out_f32_dev, M, N, N, 32, 32, true));
+        if (e == EPI_RESID_F32) TRY(make_tmap(&maps.resid, resid_dev, M, N, N, 32, 32, true));
+        else maps.resid = maps.out;
+        return launch_gemm2_tc(nullptr, e, maps, p, static_cast<cudaStream_t>(stream), prop.multiProcessorCount);
+    }
     return launch_gemm_tc(nullptr, epilogue, tmA, tmA, tmB, p, static_cast<cudaStream_t>(stream), prop.multiProcessorCount);
 }
