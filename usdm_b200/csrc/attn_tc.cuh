@@ -8,9 +8,13 @@
 //     O += P V                        tcgen05.mma  M=128 N=64  K=128, P staged in smem as bf16 (K-major, swizzled by hand),
 //                                     V tile used in place as an MN-major operand
 // q is pre-scaled by head_dim^-0.5 (folded into W_q / b_q at weight-finalise time, exact: 2^-3).
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 softmax of query half A, warps 6..9
-// softmax of query half B (thread == query row == TMEM lane).  The MMA warp ping-pongs between the halves so that the
-// tensor pipe works on one half while the other half's softmax runs; K/V tiles are shared by both halves.
+// Warp roles (384 threads = 3 warpgroups): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocation (warpgroup 0
+// gives most of its registers back with setmaxnreg), warps 4..7 softmax of query half A, warps 8..11 softmax of query
+// half B (thread == query row == TMEM lane; setmaxnreg raises them to 216 registers so a 128-column score row lives in
+// registers without spilling).  The MMA warp ping-pongs between the halves so that the tensor pipe works on one half
+// while the other half's softmax runs; K/V tiles are shared by both halves.
+// PTMEM = true keeps P in tensor memory (bf16 pairs written with tcgen05.st over the dead S columns, consumed as the
+// TMEM A operand of the PV MMA); PTMEM = false stages P through shared memory.
 // TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
 //
 // Off-diagonal key blocks have a known sign of (i - j), so the bias is affine in j and is evaluated with packed
@@ -30,7 +34,7 @@ constexpr int ATT_SMEM_KV = 2 * ATT_TILE_BYTES;                               //
 constexpr int ATT_SMEM_P = ATT_SMEM_KV + ATT_KV_STAGES * 2 * ATT_TILE_BYTES;  // 2 halves x 32 KB
 constexpr int ATT_SMEM_BAR = ATT_SMEM_P + 4 * ATT_TILE_BYTES;
 constexpr int ATT_SMEM_BYTES = ATT_SMEM_BAR + 256;
-constexpr int ATT_THREADS = 320;
+constexpr int ATT_THREADS = 384;   // warpgroup 0: TMA / MMA / TMEM-alloc warps (+1 idle), warpgroups 1-2: softmax of query halves A / B
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ uint64_t pack2f(float lo, float hi) {
@@ -57,6 +61,7 @@ __device__ __forceinline__ float ex2_approx(float x) {      // 2^x, MUFU.EX2; in
     return y;
 }
 
+template <bool PTMEM>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ ctx, int H, const float* __restrict__ slopes,
                const int4* __restrict__ work) {
@@ -91,6 +96,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    if (warp_idx < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp_idx == 0) {
         // ------------------------------------------ TMA producer ------------------------------------------
         if (lane == 0) {
@@ -127,10 +134,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
                 const uint32_t sPh = sP + half * 2 * ATT_TILE_BYTES;
 #pragma unroll
                 for (int k = 0; k < ATT_BK / 16; ++k) {
-                    // A: P half-tile (k / 4), 32 B per K step inside the swizzle atom.  B: V rows [16k, 16k+16) -> 2048 B per K step.
-                    const uint64_t da = make_smem_desc_sw128(sPh + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024);
+                    // B: V rows [16k, 16k+16) -> 2048 B per K step.
                     const uint64_t db = make_smem_desc_sw128(sV + k * 2048, 8192, 1024);
-                    umma_ss(tmem_base + 256 + half * 64, da, db, idesc_pv, (j | k) != 0);
+                    if constexpr (PTMEM) {
+                        // A: P in TMEM over the first 64 columns of this half's S region, 8 columns (16 bf16) per K step
+                        umma_ts(tmem_base + 256 + half * 64, tmem_base + half * 128 + k * 8, db, idesc_pv, (j | k) != 0);
+                    } else {
+                        // A: P half-tile (k / 4) in smem, 32 B per K step inside the swizzle atom
+                        const uint64_t da = make_smem_desc_sw128(sPh + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024);
+                        umma_ss(tmem_base + 256 + half * 64, da, db, idesc_pv, (j | k) != 0);
+                    }
                 }
             };
             mbar_wait(q_full, 0);
@@ -167,9 +180,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
                 slot = nslot; phase = nphase;
             }
         }
+    }
     } else {
         // ------------------------------ softmax + epilogue: one thread per query row ------------------------------
-        const int half = (warp_idx - 2) >> 2;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+        const int half = (warp_idx - 4) >> 2;
         if (half == 0 || two) {
             const int quad = warp_idx & 3;
             const int r = quad * 32 + lane;                 // row inside the half == TMEM lane
@@ -264,14 +279,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
                         acc2 = fadd2(acc2, pack2f(lo, hi));
                         pk[u] = pack_bf16x2(lo, hi);
                     }
-                    // keys [8g, 8g+8): half-tile (g >> 3), chunk (g & 7)
-                    const int chunk = (g & 7) ^ (r & 7);
-                    *reinterpret_cast<uint4*>(sP + (g >> 3) * ATT_TILE_BYTES + chunk * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    if constexpr (PTMEM) {
+                        // bf16 pairs (keys 2c, 2c+1) -> 32-bit column c of this row's P, over the dead S columns
+                        s[g * 4 + 0] = pk[0]; s[g * 4 + 1] = pk[1]; s[g * 4 + 2] = pk[2]; s[g * 4 + 3] = pk[3];
+                    } else {
+                        // keys [8g, 8g+8): half-tile (g >> 3), chunk (g & 7)
+                        const int chunk = (g & 7) ^ (r & 7);
+                        *reinterpret_cast<uint4*>(sP + (g >> 3) * ATT_TILE_BYTES + chunk * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+                if constexpr (PTMEM) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) tmem_st_32x16(tmem_S + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&s[c * 16]));
+                    tmem_st_wait();
                 }
                 float a0, a1;
                 unpack2f(acc2, a0, a1);
                 l_run += a0 + a1;
-                fence_proxy_async_smem();
+                if constexpr (!PTMEM) fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive(&p_ready[half]);
             }
@@ -310,15 +335,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
 }
 
 inline cudaError_t launch_attn_tc_raw(const CUtensorMap& tmQKV, __nv_bfloat16* ctx, int H, int nheads, const float* slopes,
-                                      const int4* work, int nwork, cudaStream_t st) {
+                                      const int4* work, int nwork, bool p_in_tmem, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr = true;
     }
     dim3 grid(nwork, nheads);
-    attn_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, ctx, H, slopes, work);
+    if (p_in_tmem) attn_tc_kernel<true><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, ctx, H, slopes, work);
+    else           attn_tc_kernel<false><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, ctx, H, slopes, work);
     return cudaGetLastError();
 }
 

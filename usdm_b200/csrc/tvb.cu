@@ -121,6 +121,7 @@ struct tvb_handle {
     int opt_attn_tc = 1;        // bf16 path: 1 = tcgen05 attention, 0 = CUDA-core attention (ablation / cross-check)
     int opt_conv_tc = 1;        // bf16 path: 1 = tcgen05 positional conv, 0 = CUDA-core conv
     int opt_gemm_2cta = 1;      // bf16 path: 1 = CTA-pair (cta_group::2) GEMM, 0 = single-CTA GEMM
+    int opt_attn_ptmem = 1;     // tcgen05 attention: 1 = P kept in tensor memory (TS MMA), 0 = P staged through shared memory
     int profile = 0;            // 1: bracket every kernel with CUDA events on the launching stream (bench.py roofline leg)
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -481,6 +482,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     if (!strcmp(name, "attn_tc")) h->opt_attn_tc = value ? 1 : 0;
     else if (!strcmp(name, "conv_tc")) h->opt_conv_tc = value ? 1 : 0;
     else if (!strcmp(name, "gemm_2cta")) h->opt_gemm_2cta = value ? 1 : 0;
+    else if (!strcmp(name, "attn_ptmem")) h->opt_attn_ptmem = value ? 1 : 0;
     else if (!strcmp(name, "profile")) { h->profile = value ? 1 : 0; h->ev_used = 0; h->ev_cat.clear(); }
     else return fail(TVB_ERR_INVALID, "unknown option %s", name);
     return TVB_OK;
@@ -735,7 +737,7 @@ static int attention(tvb_handle* h, cudaStream_t st) {
     const int H = h->cfg.hidden_size, nh = h->cfg.num_attention_heads;
     ProfScope ps(h, st, PC_ATTN);
     if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc) {
-        CK(launch_attn_tc_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, st));
+        CK(launch_attn_tc_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_ptmem != 0, st));
     } else if (h->precision == TVB_PRECISION_BF16) {
         dim3 grid(h->n_work16, nh);
         k_attn_simt<bf16><<<grid, 128, 0, st>>>(h->qkv.b16, h->ctx.b16, h->L, H, h->slopes, h->d_work16);
