@@ -69,8 +69,9 @@ def generate_sharded(generate_fn: Callable, x: torch.Tensor, cond: torch.Tensor,
     if world == 1:
         gathered = local.unsqueeze(0)
     else:
-        gathered = torch.empty((world, n_max, M, T), dtype=torch.float32, device=cond.device)
-        dist.all_gather_into_tensor(gathered, local, group=group)
+        flat = torch.empty((world * n_max, M, T), dtype=torch.float32, device=cond.device)   # dim-0 concat: valid for NCCL and gloo
+        dist.all_gather_into_tensor(flat, local, group=group)
+        gathered = flat.view(world, n_max, M, T)
     full = torch.zeros((N, M, T), dtype=torch.float32, device=cond.device)
     for r, s in enumerate(shards):
         if s:
