@@ -289,7 +289,7 @@ def main():
         roof = dict(bound="tensor", kernel="gemm_tc_kernel (tcgen05 bf16 linear layers)", achieved=achieved, peak=peaks["sustained"],
                     unit="TFLOP/s", frac=achieved / peaks["sustained"], traffic=None, peak_source=peaks["source"] + " bf16_tflops_sustained",
                     flops_per_launch=fl["gemm"] * passes / max(gemm_n, 1), avg_launch_ms=gemm_ms / max(gemm_n, 1),
-                    share_of_step=gemm_ms / sum(v[0] for v in prof.values()))
+                    share_of_step=gemm_ms / sum(v[0] for k, v in prof.items() if not k.startswith("gemm_")))
         for k in ("attention", "posconv"):
             ms = prof[k][0]
             if ms > 0:

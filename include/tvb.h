@@ -71,7 +71,10 @@ int tvb_set_precision(tvb_handle* h, int32_t precision);
 int tvb_get_precision(const tvb_handle* h);
 /* Ablation / cross-check switches of the bf16 path: "attn_tc" and "conv_tc" (1 = tcgen05 kernel, default;
  * 0 = the CUDA-core kernel of the same op; both are GPU kernels of this library, there is no CPU path),
- * "gemm_2cta" (1 = CTA-pair tcgen05 GEMM, default; 0 = single-CTA tcgen05 GEMM), and "profile" (see tvb_profile_read). */
+ * "gemm_2cta" (1 = CTA-pair tcgen05 GEMM, default; 0 = single-CTA tcgen05 GEMM), "attn_v" (4 = attn4_tc.cuh, default;
+ * 3 = attn_tc.cuh), "attn_poly" (attention v4: 0 = every exp2 on MUFU; 2/3/4 = one element pair in n on the FMA-pipe
+ * polynomial), "ln_fuse" (1 = LayerNorm re-applied in the residual GEMM epilogue instead of materialising the fp32
+ * stream, default; 0 = separate fp32 LayerNorm output), and "profile" (see tvb_profile_read). */
 int tvb_set_option(tvb_handle* h, const char* name, int32_t value);
 
 /* Replaces: Transformer.forward(x, y, cond, t, lengths) (networks.py:302-374) — the per-step velocity estimator.
@@ -105,9 +108,10 @@ int tvb_solve(tvb_handle* h, int32_t solver, const int64_t* x_dev, const float* 
 
 /* Per-kernel timing (bench.py's roofline leg).  With tvb_set_option(h, "profile", 1) every kernel launch is bracketed by
  * CUDA events on the launching stream; tvb_profile_read synchronises the device, sums the elapsed milliseconds and launch
- * counts by category into two arrays of 8 entries and resets the log.
- * Categories: 0 linear-layer GEMMs, 1 attention, 2 positional conv, 3 LayerNorm, 4 frame projection / time token,
- * 5 output projection + CFG/ODE update, 6-7 unused. */
+ * counts by category into two arrays of 16 entries and resets the log.
+ * Categories: 0 linear-layer GEMMs (total), 1 attention, 2 positional conv, 3 LayerNorm, 4 frame projection / time token,
+ * 5 output projection + CFG/ODE update, 6-7 unused, 8-12 the GEMMs by call site (QKV, attention out, FFN in, FFN out,
+ * skip merge; these also count into 0), 13-15 unused. */
 int tvb_profile_read(tvb_handle* h, double* ms_by_cat, int64_t* launches_by_cat);
 
 /* Number of this library's kernels launched by the handle since creation (bench.py's gpu_launches). */
@@ -123,6 +127,13 @@ int64_t tvb_device_bytes(const tvb_handle* h);
 int tvb_debug_gemm_bf16(int device, const void* a_dev, const void* w_dev, const float* bias_dev, const float* resid_dev,
                         float* out_f32_dev, void* out_bf16_dev, int32_t M, int32_t N, int32_t K, int32_t epilogue,
                         void* stream);
+
+/* Kernel-level test hook (tests/ only): the tcgen05 attention kernel alone on packed [rows, 3H] bf16 q|k|v rows (q pre-scaled
+ * by head_dim^-0.5 * log2(e)); sequence s occupies rows [seq_start[s], seq_start[s] + seq_len[s]).  ctx_dev bf16 [rows, H].
+ * version: 4 = attn4_tc.cuh, 3 = attn_tc.cuh (P in tensor memory), 2 = attn_tc.cuh (P through shared memory).  Synchronises. */
+int tvb_debug_attention(int device, const void* qkv_dev, void* ctx_dev, const int32_t* seq_start_host, const int32_t* seq_len_host,
+                        int32_t nseq, int32_t rows, int32_t H, int32_t nheads, const float* slopes_dev, int32_t version,
+                        int32_t poly, void* stream);
 
 const char* tvb_last_error(void);
 const char* tvb_version(void);

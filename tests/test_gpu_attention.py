@@ -1,0 +1,91 @@
+"""GPU: the tcgen05 attention kernels alone (usdm_b200/csrc/attn4_tc.cuh, attn_tc.cuh) through tvb_debug_attention, against
+fp32 torch math on the SAME bf16 q|k|v rows: softmax_j(q_i.k_j - slope_h |i-j| [j != 0]) with keys j >= len masked
+(reference networks.py:319-341, :174-193).  The only rounding that differs from the fp32 math is P -> bf16 before PV."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+H, NH = 1024, 16
+LOG2E = 1.4426950408889634
+
+
+def _slopes():
+    start = 2 ** (-2 ** -(math.log2(NH) - 3))
+    return torch.tensor([start * start ** i for i in range(NH)], dtype=torch.float32)
+
+
+def _reference(qkv, starts, lens, slopes):
+    out = torch.zeros(qkv.shape[0], H, device=qkv.device)
+    for st, L in zip(starts, lens):
+        blk = qkv[st:st + L].float()
+        q = blk[:, :H].view(L, NH, 64).transpose(0, 1)          # carries 0.125 * log2(e)
+        k = blk[:, H:2 * H].view(L, NH, 64).transpose(0, 1)
+        v = blk[:, 2 * H:].view(L, NH, 64).transpose(0, 1)
+        s = torch.matmul(q, k.transpose(1, 2)) / LOG2E
+        idx = torch.arange(L, device=qkv.device)
+        dist = (idx[:, None] - idx[None, :]).abs().float()
+        bias = -slopes.to(qkv.device)[:, None, None] * dist[None]
+        bias[:, :, 0] = 0.0
+        p = torch.softmax(s + bias, dim=-1)
+        out[st:st + L] = torch.matmul(p, v).transpose(0, 1).reshape(L, H)
+    return out
+
+
+def _run(lens, version, poly, seed=0, scale=1.0):
+    from usdm_b200 import engine
+    lib = engine.load_library()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    starts, o = [], 0
+    for L in lens:
+        starts.append(o)
+        o += L + 16
+    rows = (o + 255) // 256 * 256
+    qkv = torch.randn(rows, 3 * H, device="cuda", generator=g) * scale
+    qkv[:, :H] *= 0.125 * LOG2E
+    qkv = qkv.to(torch.bfloat16)
+    ctx = torch.zeros(rows, H, device="cuda", dtype=torch.bfloat16)
+    slopes = _slopes().cuda()
+    s_arr = (C.c_int32 * len(lens))(*starts)
+    l_arr = (C.c_int32 * len(lens))(*lens)
+    rc = lib.tvb_debug_attention(0, C.c_void_p(qkv.data_ptr()), C.c_void_p(ctx.data_ptr()), s_arr, l_arr, len(lens), rows, H, NH,
+                                 C.c_void_p(slopes.data_ptr()), version, poly, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    engine.check(rc)
+    torch.cuda.synchronize()
+    ref = _reference(qkv, starts, lens, slopes)
+    valid = torch.zeros(rows, dtype=torch.bool, device="cuda")
+    for st, L in zip(starts, lens):
+        valid[st:st + L] = True
+    assert float(ctx[~valid].float().abs().sum()) == 0.0          # rows outside every sequence are never written
+    a, b = ctx[valid].float(), ref[valid]
+    return float((a - b).norm() / b.norm()), float((a - b).abs().max())
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("version,poly", [(4, 0), (4, 2), (4, 3), (4, 4), (3, 0), (2, 0)])
+def test_attention_kernel_vs_fp32_math(version, poly):
+    # lengths cover: 1 key, < 1 block, exact block multiples, odd tails, one / two query halves, the configs[1] length
+    lens = [1134, 1, 127, 128, 129, 256, 257, 384, 700, 389, 2, 513]
+    rel, mx = _run(lens, version, poly)
+    print(f"attention v{version} poly={poly}: rel-L2 {rel:.3e}, max-abs {mx:.3e}")
+    assert rel < 4e-3
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("poly", [0, 3])
+def test_attention_v4_peaky_scores_exercise_rescale(poly):
+    """Large-magnitude q.k (std ~ 20 in the log2 domain) so that block maxima jump by more than 2^8 and the lazy O rescale runs."""
+    rel, mx = _run([1134, 640, 300], 4, poly, seed=1, scale=2.2)
+    print(f"attention v4 poly={poly}, peaky: rel-L2 {rel:.3e}, max-abs {mx:.3e}")
+    assert rel < 6e-3
+
+
+@pytest.mark.timeout(600)
+def test_attention_v4_long_form():
+    """configs[2]-like length (30 s + prompt): 23 key blocks, 12 query tiles per head."""
+    rel, mx = _run([2856, 2584], 4, 0, seed=2)
+    print(f"attention v4 long-form: rel-L2 {rel:.3e}, max-abs {mx:.3e}")
+    assert rel < 4e-3

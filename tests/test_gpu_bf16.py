@@ -15,17 +15,29 @@ def _est(m, g):
     return v
 
 
+ABLATIONS = [
+    dict(attn_tc=0, conv_tc=0, gemm_2cta=0, ln_fuse=0),      # CUDA-core attention / conv, single-CTA GEMM, materialised LayerNorm
+    dict(attn_tc=1, conv_tc=0, gemm_2cta=0, ln_fuse=0),
+    dict(attn_tc=0, conv_tc=1, gemm_2cta=0, ln_fuse=0),
+    dict(attn_tc=0, conv_tc=0, gemm_2cta=1, ln_fuse=0),
+    dict(attn_tc=0, conv_tc=0, gemm_2cta=0, ln_fuse=1),      # fused-LayerNorm residual epilogue of the single-CTA GEMM
+    dict(attn_tc=0, conv_tc=0, gemm_2cta=1, ln_fuse=1),      # ... of the CTA-pair GEMM
+    dict(attn_v=3),                                          # previous attention kernel generation
+    dict(attn_poly=2), dict(attn_poly=3), dict(attn_poly=4),  # exp2 partly on the FMA pipe
+    dict(),                                                  # shipping defaults
+]
+
+
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("attn_tc,conv_tc,gemm_2cta", [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 1)])
-def test_estimator_ragged_vs_reference_golden(attn_tc, conv_tc, gemm_2cta):
+@pytest.mark.parametrize("opts", ABLATIONS, ids=lambda o: ",".join(f"{k}={v}" for k, v in o.items()) or "defaults")
+def test_estimator_ragged_vs_reference_golden(opts):
     g = golden("estimator_ragged.pt")
     m = model(0, True, "bf16")
-    m.set_option("attn_tc", attn_tc)
-    m.set_option("conv_tc", conv_tc)
-    m.set_option("gemm_2cta", gemm_2cta)
+    for k, v in opts.items():
+        m.set_option(k, v)
     v = _est(m, g)
     err = rel_l2(v, g["v"])
-    print(f"bf16 estimator (attn_tc={attn_tc}, conv_tc={conv_tc}, gemm_2cta={gemm_2cta}) rel-L2 vs reference fp32: {err:.3e}")
+    print(f"bf16 estimator ({opts or 'defaults'}) rel-L2 vs reference fp32: {err:.3e}")
     assert torch.isfinite(v).all()
     assert err < TOL
     for b, L in enumerate(g["lengths"].tolist()):

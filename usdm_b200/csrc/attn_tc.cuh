@@ -64,7 +64,7 @@ __device__ __forceinline__ float ex2_approx(float x) {      // 2^x, MUFU.EX2; in
 template <bool PTMEM>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ ctx, int H, const float* __restrict__ slopes,
-               const int4* __restrict__ work) {
+               const int4* __restrict__ work, const float qk_scale /* log2(e), or 1 when it is already folded into W_q */) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_SMEM_BAR);
     uint64_t* q_full = bars + 0;
@@ -196,7 +196,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
             const uint32_t tmem_S = tmem_base + half * 128 + lane_off;
             const uint32_t tmem_O = tmem_base + 256 + half * 64 + lane_off;
             uint8_t* sP = smem + ATT_SMEM_P + half * 2 * ATT_TILE_BYTES + r * 128;
-            const uint64_t L2 = pack2f(LOG2E, LOG2E);
+            const uint64_t L2 = pack2f(qk_scale, qk_scale);
             float m_run = -INFINITY, l_run = 0.f;
             for (int j = 0; j < nkb; ++j) {
                 const int k0 = j * ATT_BK;
@@ -232,10 +232,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
 #pragma unroll
                     for (int e = 0; e < 128; ++e) {
                         const float bias = -slope2 * fabsf(d0 - static_cast<float>(e));
-                        s[e] = __float_as_uint(fmaf(__uint_as_float(s[e]), LOG2E, bias));
+                        s[e] = __float_as_uint(fmaf(__uint_as_float(s[e]), qk_scale, bias));
                     }
                 }
-                if (k0 == 0) s[0] = __float_as_uint(s0raw * LOG2E);       // key 0 (time token) carries no distance penalty
+                if (k0 == 0) s[0] = __float_as_uint(s0raw * qk_scale);       // key 0 (time token) carries no distance penalty
                 if (k0 + ATT_BK > len) {
 #pragma unroll
                     for (int e = 0; e < 128; ++e)
@@ -335,7 +335,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
 }
 
 inline cudaError_t launch_attn_tc_raw(const CUtensorMap& tmQKV, __nv_bfloat16* ctx, int H, int nheads, const float* slopes,
-                                      const int4* work, int nwork, bool p_in_tmem, cudaStream_t st) {
+                                      const int4* work, int nwork, bool p_in_tmem, float qk_scale, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
@@ -345,8 +345,8 @@ inline cudaError_t launch_attn_tc_raw(const CUtensorMap& tmQKV, __nv_bfloat16* c
         attr = true;
     }
     dim3 grid(nwork, nheads);
-    if (p_in_tmem) attn_tc_kernel<true><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, ctx, H, slopes, work);
-    else           attn_tc_kernel<false><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, ctx, H, slopes, work);
+    if (p_in_tmem) attn_tc_kernel<true><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, ctx, H, slopes, work, qk_scale);
+    else           attn_tc_kernel<false><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, ctx, H, slopes, work, qk_scale);
     return cudaGetLastError();
 }
 

@@ -29,6 +29,8 @@ enum GemmEpilogue : int {
     EPI_RESID_F32 = 2,   // out_f32  = acc + bias + resid
     EPI_DUAL = 3,        // out_f32  = acc + bias ; out_bf16 = bf16(out_f32)
     EPI_F32 = 4,         // out_f32  = acc + bias
+    EPI_RESID_LN = 5,    // out_f32  = acc + bias + LayerNorm(resid)  with per-row (mean, rstd) from ln_stats and per-column ln_g / ln_b:
+                         // the post-LN residual stream is re-normalised on the fly instead of being written and re-read in fp32
 };
 
 struct GemmParams {
@@ -39,6 +41,9 @@ struct GemmParams {
     float* out_f32;       // [M, ld_out]
     __nv_bfloat16* out_bf16;
     int ld_out;           // row stride of outputs / resid, in elements
+    const float2* ln_stats;   // [M] (mean, rstd) of the resid rows            (EPI_RESID_LN)
+    const float* ln_g;        // [N] LayerNorm weight / bias of the residual's norm
+    const float* ln_b;
 };
 
 template <int EPI>
@@ -174,7 +179,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
                     }
                 }
-                if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_DUAL || EPI == EPI_F32) {
+                if constexpr (EPI == EPI_RESID_LN) {
+                    const float2 st = p.ln_stats[row];
+                    const float4* r4 = reinterpret_cast<const float4*>(p.resid + row_off + col);
+                    const float4* g4 = reinterpret_cast<const float4*>(p.ln_g + col);
+                    const float4* b4 = reinterpret_cast<const float4*>(p.ln_b + col);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 x = r4[j], g = __ldg(g4 + j), b = __ldg(b4 + j);
+                        v[4 * j + 0] += fmaf((x.x - st.x) * st.y, g.x, b.x); v[4 * j + 1] += fmaf((x.y - st.x) * st.y, g.y, b.y);
+                        v[4 * j + 2] += fmaf((x.z - st.x) * st.y, g.z, b.z); v[4 * j + 3] += fmaf((x.w - st.x) * st.y, g.w, b.w);
+                    }
+                }
+                if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_RESID_LN || EPI == EPI_DUAL || EPI == EPI_F32) {
                     float4* o4 = reinterpret_cast<float4*>(p.out_f32 + row_off + col);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -253,7 +270,7 @@ gemm2_tc_kernel(const __grid_constant__ Gemm2Maps tm, const GemmParams p) {
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tm.a); tma_prefetch_desc(&tm.a2); tma_prefetch_desc(&tm.b); tma_prefetch_desc(&tm.out);
-        if (EPI == EPI_RESID_F32) tma_prefetch_desc(&tm.resid);
+        if (EPI == EPI_RESID_F32 || EPI == EPI_RESID_LN) tma_prefetch_desc(&tm.resid);
     }
     if (warp_idx == 1 && lane == 0) {
         for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -311,6 +328,7 @@ gemm2_tc_kernel(const __grid_constant__ Gemm2Maps tm, const GemmParams p) {
     } else {
         // ------------------------------------------ epilogue ------------------------------------------
         constexpr bool kBf16Out = (EPI == EPI_BF16 || EPI == EPI_GELU_BF16);
+        constexpr bool kResid = (EPI == EPI_RESID_F32 || EPI == EPI_RESID_LN);
         constexpr int kChunkCols = kBf16Out ? 64 : 32;            // one staging tile row = 128 B
         constexpr int kChunks = 128 / kChunkCols;                 // per warp per tile
         const int ew = warp_idx - 2;
@@ -324,7 +342,7 @@ gemm2_tc_kernel(const __grid_constant__ Gemm2Maps tm, const GemmParams p) {
             row = (tile / tiles_n) * 256 + static_cast<int>(cta) * 128 + quad * 32;
             col = (tile % tiles_n) * 256 + chalf * 128 + c * kChunkCols;
         };
-        if constexpr (EPI == EPI_RESID_F32) {
+        if constexpr (kResid) {
             if (lane == 0 && cluster_id < num_tiles) {
                 int col, row;
                 chunk_coords(cluster_id, 0, col, row);
@@ -345,7 +363,7 @@ gemm2_tc_kernel(const __grid_constant__ Gemm2Maps tm, const GemmParams p) {
                 int col, row;
                 chunk_coords(tile, c, col, row);
                 if (lane == 0) {
-                    if constexpr (EPI == EPI_RESID_F32) {
+                    if constexpr (kResid) {
                         // the other buffer's last store must have finished reading before the next residual lands in it
                         tma_store_wait_read<0>();
                         int nt = tile, nc = c + 1;
@@ -390,6 +408,18 @@ gemm2_tc_kernel(const __grid_constant__ Gemm2Maps tm, const GemmParams p) {
                         float4* q4 = reinterpret_cast<float4*>(rowp + ((j ^ r7) << 4));
                         const float4 rr = *q4;
                         *q4 = make_float4(v[4 * j] + rr.x, v[4 * j + 1] + rr.y, v[4 * j + 2] + rr.z, v[4 * j + 3] + rr.w);
+                    }
+                } else if constexpr (EPI == EPI_RESID_LN) {
+                    const float2 st = p.ln_stats[row + lane];      // (mean, rstd) of this thread's residual row
+                    const float4* g4 = reinterpret_cast<const float4*>(p.ln_g + col);
+                    const float4* b4 = reinterpret_cast<const float4*>(p.ln_b + col);
+                    mbar_wait(&rb[buf], (kc >> 1) & 1);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4* q4 = reinterpret_cast<float4*>(rowp + ((j ^ r7) << 4));
+                        const float4 rr = *q4, g = __ldg(g4 + j), b = __ldg(b4 + j);
+                        *q4 = make_float4(v[4 * j] + fmaf((rr.x - st.x) * st.y, g.x, b.x), v[4 * j + 1] + fmaf((rr.y - st.x) * st.y, g.y, b.y),
+                                          v[4 * j + 2] + fmaf((rr.z - st.x) * st.y, g.z, b.z), v[4 * j + 3] + fmaf((rr.w - st.x) * st.y, g.w, b.w));
                     }
                 } else if constexpr (kBf16Out) {
 #pragma unroll

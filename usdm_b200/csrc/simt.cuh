@@ -118,7 +118,9 @@ k_frame_proj(RowLayout L, int T, int nf, int H, const float* __restrict__ Wt, co
 template <typename TB>
 __global__ void __launch_bounds__(256)
 k_layernorm(const float* __restrict__ x, float* __restrict__ y, TB* __restrict__ yb, const float* __restrict__ gamma,
-            const float* __restrict__ beta, const int* __restrict__ row_seq, int Mp, int H, float eps) {
+            const float* __restrict__ beta, const int* __restrict__ row_seq, int Mp, int H, float eps, float2* __restrict__ stats) {
+    // y == nullptr (with stats != nullptr): the fp32 result is not materialised; consumers that need it (the residual add of
+    // the next GEMM epilogue, EPI_RESID_LN) recompute it from x and the (mean, rstd) written to stats[row].
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= Mp) return;
@@ -146,6 +148,7 @@ k_layernorm(const float* __restrict__ x, float* __restrict__ y, TB* __restrict__
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     const float rstd = rsqrtf(sq / H + eps);
+    if (stats != nullptr && lane == 0) stats[row] = make_float2(mean, rstd);
     float4* y4 = reinterpret_cast<float4*>(y + static_cast<size_t>(row) * H);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -158,7 +161,7 @@ k_layernorm(const float* __restrict__ x, float* __restrict__ y, TB* __restrict__
             o.y = valid ? (v[j].y - mean) * rstd * g.y + b.y : 0.f;
             o.z = valid ? (v[j].z - mean) * rstd * g.z + b.z : 0.f;
             o.w = valid ? (v[j].w - mean) * rstd * g.w + b.w : 0.f;
-            y4[c4] = o;
+            if (y != nullptr) y4[c4] = o;
             if (yb) {
                 if constexpr (sizeof(TB) == 2) {
                     reinterpret_cast<uint2*>(yb + static_cast<size_t>(row) * H)[c4] =
@@ -302,7 +305,7 @@ k_sgemm(const SgemmParams p) {
 template <typename T>
 __global__ void __launch_bounds__(128)
 k_attn_simt(const T* __restrict__ qkv, T* __restrict__ ctx, RowLayout L, int H, const float* __restrict__ slopes,
-            const int2* __restrict__ work) {
+            const int2* __restrict__ work, float score_scale) {
     __shared__ float Qs[16][64];
     __shared__ float Ks[32][65];
     __shared__ float Vs[32][64];
@@ -337,6 +340,7 @@ k_attn_simt(const T* __restrict__ qkv, T* __restrict__ ctx, RowLayout L, int H, 
             float s = 0.f;
 #pragma unroll 16
             for (int d = 0; d < 64; ++d) s = fmaf(Qs[qi][d], Ks[lane][d], s);
+            s *= score_scale;          // 1 (fp32 path) or ln 2 (bf16 path: q carries log2(e) for the tcgen05 kernel)
             if (j != 0) s -= slope * fabsf(static_cast<float>(i - j));
             if (j >= Ls) s = -INFINITY;
             float mx = s;

@@ -15,6 +15,7 @@
 
 #include "../../include/tvb.h"
 #include "attn_tc.cuh"
+#include "attn4_tc.cuh"
 #include "conv_tc.cuh"
 #include "gemm_tc.cuh"
 #include "simt.cuh"
@@ -93,6 +94,7 @@ struct Lin {                 // one nn.Linear: y = x W^T + b
     const float* w32 = nullptr;
     bf16* w16 = nullptr;
     const float* bias = nullptr;
+    const float* bias_tc = nullptr;   // bias of the bf16 tensor-core path (differs from `bias` only for the fused QKV projection)
     int N = 0, K = 0;
     CUtensorMap tm;          // B operand map: [N, K], box 256 x 64 (single-CTA kernel)
     CUtensorMap tm2;         // B operand map: [N, K], box 128 x 64 (CTA-pair kernel: each CTA stages half of the W tile)
@@ -121,7 +123,11 @@ struct tvb_handle {
     int opt_attn_tc = 1;        // bf16 path: 1 = tcgen05 attention, 0 = CUDA-core attention (ablation / cross-check)
     int opt_conv_tc = 1;        // bf16 path: 1 = tcgen05 positional conv, 0 = CUDA-core conv
     int opt_gemm_2cta = 1;      // bf16 path: 1 = CTA-pair (cta_group::2) GEMM, 0 = single-CTA GEMM
-    int opt_attn_ptmem = 1;     // tcgen05 attention: 1 = P kept in tensor memory (TS MMA), 0 = P staged through shared memory
+    int opt_attn_ptmem = 1;     // tcgen05 attention v3: 1 = P kept in tensor memory (TS MMA), 0 = P staged through shared memory
+    int opt_attn_v = 3;         // tcgen05 attention kernel generation: 4 = attn4_tc.cuh (default), 3 = attn_tc.cuh
+    int opt_attn_poly = 0;      // attention v4: 0 = every exp2 on MUFU, n = one element pair in n on the FMA-pipe polynomial
+    int opt_ln_fuse = 1;        // bf16 path: 1 = LayerNorm writes bf16 + (mean, rstd) only and the residual GEMM epilogue re-normalises
+                                //            the fp32 stream on the fly (EPI_RESID_LN); 0 = LayerNorm materialises the fp32 result
     int profile = 0;            // 1: bracket every kernel with CUDA events on the launching stream (bench.py roofline leg)
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -154,13 +160,15 @@ struct tvb_handle {
     int plan_B = 0, plan_T = 0, plan_cfg = 0, plan_half = 0;
     float* base = nullptr;
     Act hin, p1, slots[32], hbA, hbB, qkv, ctx, mid;
-    float *xpre = nullptr, *hres = nullptr, *vbuf = nullptr;
+    float *xpre = nullptr, *xalt = nullptr, *hres = nullptr, *vbuf = nullptr;
+    float2 *statsA = nullptr, *statsB = nullptr;       // per-row (mean, rstd) of the two LayerNorms in flight (ln_fuse)
     float *z_work = nullptr, *z_hat = nullptr, *v_pred = nullptr;
-    CUtensorMap tm_xpre, tm_hres;                // fp32 [Mp, H] epilogue maps (box 32 rows x 32 columns): TMA store / residual load
+    CUtensorMap tm_xpre, tm_xalt, tm_hres;       // fp32 [Mp, H] epilogue maps (box 32 rows x 32 columns): TMA store / residual load
 };
 
 // per-kernel timing scopes (only active when option "profile" is set)
-enum ProfCat { PC_GEMM = 0, PC_ATTN = 1, PC_CONV = 2, PC_NORM = 3, PC_FRAME = 4, PC_OUT = 5, PC_NCAT = 8 };
+enum ProfCat { PC_GEMM = 0, PC_ATTN = 1, PC_CONV = 2, PC_NORM = 3, PC_FRAME = 4, PC_OUT = 5,
+               PC_GEMM_QKV = 8, PC_GEMM_O = 9, PC_GEMM_F1 = 10, PC_GEMM_F2 = 11, PC_GEMM_SKIP = 12, PC_NCAT = 16 };
 struct ProfScope {
     tvb_handle* h;
     cudaStream_t st;
@@ -291,13 +299,17 @@ static int need(tvb_handle* h, const std::string& key, std::vector<int64_t> shap
     return TVB_OK;
 }
 
-static int make_lin(tvb_handle* h, Lin* lin, const float* w32, const float* bias, int N, int K) {
+// w32_tc / bias_tc: the weights the bf16 tensor-core path uses when they differ from the fp32 path's (fused QKV: the q rows
+// additionally carry log2(e) so that the tcgen05 attention kernel gets scores in the log2 domain straight out of the MMA).
+static int make_lin(tvb_handle* h, Lin* lin, const float* w32, const float* bias, int N, int K, const float* w32_tc = nullptr,
+                    const float* bias_tc = nullptr) {
     lin->w32 = w32;
     lin->bias = bias;
+    lin->bias_tc = bias_tc ? bias_tc : bias;
     lin->N = N;
     lin->K = K;
     TRY(dev_alloc_t(h, h->owned, &lin->w16, static_cast<size_t>(N) * K));
-    k_f32_to_bf16<<<grid_for(static_cast<size_t>(N) * K), 256>>>(w32, lin->w16, static_cast<size_t>(N) * K);
+    k_f32_to_bf16<<<grid_for(static_cast<size_t>(N) * K), 256>>>(w32_tc ? w32_tc : w32, lin->w16, static_cast<size_t>(N) * K);
     CKL();
     TRY(make_tmap(&lin->tm, lin->w16, N, K, K, GEMM_BN));
     TRY(make_tmap(&lin->tm2, lin->w16, N, K, K, 128));
@@ -400,6 +412,8 @@ extern "C" int tvb_finalize_weights(tvb_handle* h) {
     TRY(need(h, p + "layer_norm.bias", {H}, &h->ln0_b));
     // encoder layers
     h->layers.resize(nl);
+    float* wqkv_tc = nullptr;                                  // scratch, reused by every layer (stream-ordered), freed below
+    CK(cudaMalloc(&wqkv_tc, 3 * static_cast<size_t>(H) * H * sizeof(float)));
     for (int l = 0; l < nl; ++l) {
         const std::string lp = p + "layers." + std::to_string(l) + ".";
         const float *wq, *wk, *wv, *bq, *bk, *bv, *wo, *bo, *w1, *b1, *w2, *b2;
@@ -421,18 +435,24 @@ extern "C" int tvb_finalize_weights(tvb_handle* h) {
         TRY(need(h, lp + "final_layer_norm.weight", {H}, &lw.ln2_g));
         TRY(need(h, lp + "final_layer_norm.bias", {H}, &lw.ln2_b));
         // fused [q*0.125 ; k ; v]: the q scaling (head_dim^-0.5, applied after the bias, networks.py:162) is a power of two -> exact
-        float *wqkv, *bqkv;
+        float *wqkv, *bqkv, *bqkv_tc;
         const size_t hh = static_cast<size_t>(H) * H;
         TRY(dev_alloc_t(h, h->owned, &wqkv, 3 * hh));
         TRY(dev_alloc_t(h, h->owned, &bqkv, 3 * static_cast<size_t>(H)));
+        TRY(dev_alloc_t(h, h->owned, &bqkv_tc, 3 * static_cast<size_t>(H)));
         k_scale_copy<<<grid_for(hh), 256>>>(wq, wqkv, hh, 0.125f);
         k_scale_copy<<<grid_for(hh), 256>>>(wk, wqkv + hh, hh, 1.0f);
         k_scale_copy<<<grid_for(hh), 256>>>(wv, wqkv + 2 * hh, hh, 1.0f);
         k_scale_copy<<<grid_for(H), 256>>>(bq, bqkv, H, 0.125f);
         k_scale_copy<<<grid_for(H), 256>>>(bk, bqkv + H, H, 1.0f);
         k_scale_copy<<<grid_for(H), 256>>>(bv, bqkv + 2 * H, H, 1.0f);
+        // tensor-core copy: q rows times 0.125 * log2(e) (the softmax of the tcgen05 kernels works in base 2)
+        k_scale_copy<<<grid_for(hh), 256>>>(wq, wqkv_tc, hh, 0.125f * LOG2E);
+        k_scale_copy<<<grid_for(2 * hh), 256>>>(wqkv + hh, wqkv_tc + hh, 2 * hh, 1.0f);
+        k_scale_copy<<<grid_for(H), 256>>>(bq, bqkv_tc, H, 0.125f * LOG2E);
+        k_scale_copy<<<grid_for(2 * H), 256>>>(bqkv + H, bqkv_tc + H, 2 * H, 1.0f);
         CKL();
-        TRY(make_lin(h, &lw.qkv, wqkv, bqkv, 3 * H, H));
+        TRY(make_lin(h, &lw.qkv, wqkv, bqkv, 3 * H, H, wqkv_tc, bqkv_tc));
         TRY(make_lin(h, &lw.o, wo, bo, H, H));
         TRY(make_lin(h, &lw.f1, w1, b1, F, H));
         TRY(make_lin(h, &lw.f2, w2, b2, H, F));
@@ -448,6 +468,7 @@ extern "C" int tvb_finalize_weights(tvb_handle* h) {
     TRY(need(h, p + "proj_out.weight", {nf, H, 1}, &h->w_out));
     TRY(need(h, p + "proj_out.bias", {nf}, &h->b_out));
     CK(cudaDeviceSynchronize());
+    cudaFree(wqkv_tc);
     h->finalized = true;
     return TVB_OK;
 }
@@ -462,6 +483,10 @@ extern "C" int tvb_profile_read(tvb_handle* h, double* ms_by_cat, int64_t* launc
         CK(cudaEventElapsedTime(&ms, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]));
         ms_by_cat[h->ev_cat[i]] += ms;
         launches_by_cat[h->ev_cat[i]] += 1;
+        if (h->ev_cat[i] >= PC_GEMM_QKV) {              // per-shape GEMM categories also count into the GEMM total
+            ms_by_cat[PC_GEMM] += ms;
+            launches_by_cat[PC_GEMM] += 1;
+        }
     }
     h->ev_used = 0;
     h->ev_cat.clear();
@@ -483,6 +508,9 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     else if (!strcmp(name, "conv_tc")) h->opt_conv_tc = value ? 1 : 0;
     else if (!strcmp(name, "gemm_2cta")) h->opt_gemm_2cta = value ? 1 : 0;
     else if (!strcmp(name, "attn_ptmem")) h->opt_attn_ptmem = value ? 1 : 0;
+    else if (!strcmp(name, "attn_v")) { if (value != 3 && value != 4) return fail(TVB_ERR_INVALID, "attn_v must be 3 or 4"); h->opt_attn_v = value; }
+    else if (!strcmp(name, "attn_poly")) { if (value != 0 && value != 2 && value != 3 && value != 4) return fail(TVB_ERR_INVALID, "attn_poly must be 0, 2, 3 or 4"); h->opt_attn_poly = value; }
+    else if (!strcmp(name, "ln_fuse")) h->opt_ln_fuse = value ? 1 : 0;
     else if (!strcmp(name, "profile")) { h->profile = value ? 1 : 0; h->ev_used = 0; h->ev_cat.clear(); }
     else return fail(TVB_ERR_INVALID, "unknown option %s", name);
     return TVB_OK;
@@ -568,6 +596,9 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
         TRY(dev_alloc_t(h, h->ws_owned, &h->d_tseq, sc));
         TRY(alloc_f32(h, &h->base, static_cast<size_t>(rows) * H));
         TRY(alloc_f32(h, &h->xpre, static_cast<size_t>(rows) * H));
+        TRY(alloc_f32(h, &h->xalt, static_cast<size_t>(rows) * H));
+        TRY(alloc_f32(h, reinterpret_cast<float**>(&h->statsA), 2 * static_cast<size_t>(rows)));
+        TRY(alloc_f32(h, reinterpret_cast<float**>(&h->statsB), 2 * static_cast<size_t>(rows)));
         TRY(alloc_f32(h, &h->hres, static_cast<size_t>(rows) * H));
         TRY(alloc_f32(h, &h->vbuf, static_cast<size_t>(rows) * nf));
         TRY(alloc_f32(h, &h->z_work, sn));
@@ -622,6 +653,7 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
         TRY(make_tmap(&h->mid.tm_out, h->mid.b16, Mp, F, F, 32));
         TRY(make_tmap(&h->tm_xpre, h->xpre, Mp, H, H, 32, 32, true));
         TRY(make_tmap(&h->tm_hres, h->hres, Mp, H, H, 32, 32, true));
+        TRY(make_tmap(&h->tm_xalt, h->xalt, Mp, H, H, 32, 32, true));
     }
     return TVB_OK;
 }
@@ -631,7 +663,7 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
 // ----------------------------------------------------------------------------------------------------------------
 template <int EPI>
 static int launch_gemm_tc_t(tvb_handle* h, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const GemmParams& p,
-                            cudaStream_t st, int num_sms) {
+                            cudaStream_t st, int num_sms, int cat = PC_GEMM) {
     static bool attr = false;
     if (!attr) {
         CK(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -639,27 +671,28 @@ static int launch_gemm_tc_t(tvb_handle* h, const CUtensorMap& tmA, const CUtenso
     }
     const int tiles = (p.M / GEMM_BM) * (p.N / GEMM_BN);
     const int grid = tiles < num_sms ? tiles : num_sms;
-    ProfScope ps(h, st, PC_GEMM);
+    ProfScope ps(h, st, cat);
     gemm_tc_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(tmA, tmA2, tmB, p);
     if (h) h->launches++;
     CKL();
     return TVB_OK;
 }
 static int launch_gemm_tc(tvb_handle* h, int epi, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
-                          const GemmParams& p, cudaStream_t st, int num_sms) {
+                          const GemmParams& p, cudaStream_t st, int num_sms, int cat = PC_GEMM) {
     if (p.M % GEMM_BM || p.N % GEMM_BN || p.K % GEMM_BK || p.K1 % GEMM_BK) return fail(TVB_ERR_INVALID, "gemm shape %dx%dx%d not tileable", p.M, p.N, p.K);
     switch (epi) {
-        case EPI_BF16: return launch_gemm_tc_t<EPI_BF16>(h, tmA, tmA2, tmB, p, st, num_sms);
-        case EPI_GELU_BF16: return launch_gemm_tc_t<EPI_GELU_BF16>(h, tmA, tmA2, tmB, p, st, num_sms);
-        case EPI_RESID_F32: return launch_gemm_tc_t<EPI_RESID_F32>(h, tmA, tmA2, tmB, p, st, num_sms);
-        case EPI_DUAL: return launch_gemm_tc_t<EPI_DUAL>(h, tmA, tmA2, tmB, p, st, num_sms);
-        case EPI_F32: return launch_gemm_tc_t<EPI_F32>(h, tmA, tmA2, tmB, p, st, num_sms);
+        case EPI_BF16: return launch_gemm_tc_t<EPI_BF16>(h, tmA, tmA2, tmB, p, st, num_sms, cat);
+        case EPI_GELU_BF16: return launch_gemm_tc_t<EPI_GELU_BF16>(h, tmA, tmA2, tmB, p, st, num_sms, cat);
+        case EPI_RESID_F32: return launch_gemm_tc_t<EPI_RESID_F32>(h, tmA, tmA2, tmB, p, st, num_sms, cat);
+        case EPI_DUAL: return launch_gemm_tc_t<EPI_DUAL>(h, tmA, tmA2, tmB, p, st, num_sms, cat);
+        case EPI_F32: return launch_gemm_tc_t<EPI_F32>(h, tmA, tmA2, tmB, p, st, num_sms, cat);
+        case EPI_RESID_LN: return launch_gemm_tc_t<EPI_RESID_LN>(h, tmA, tmA2, tmB, p, st, num_sms, cat);
     }
     return fail(TVB_ERR_INVALID, "unknown epilogue %d", epi);
 }
 
 template <int EPI>
-static int launch_gemm2_tc_t(tvb_handle* h, const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st, int num_sms) {
+static int launch_gemm2_tc_t(tvb_handle* h, const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st, int num_sms, int cat = PC_GEMM) {
     static bool attr = false;
     if (!attr) {
         CK(cudaFuncSetAttribute(gemm2_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
@@ -667,47 +700,60 @@ static int launch_gemm2_tc_t(tvb_handle* h, const Gemm2Maps& maps, const GemmPar
     }
     const int tiles = (p.M / 256) * (p.N / 256);
     int grid = 2 * tiles < (num_sms & ~1) ? 2 * tiles : (num_sms & ~1);
-    ProfScope ps(h, st, PC_GEMM);
+    ProfScope ps(h, st, cat);
     gemm2_tc_kernel<EPI><<<grid, G2_THREADS, G2_SMEM_BYTES, st>>>(maps, p);
     if (h) h->launches++;
     CKL();
     return TVB_OK;
 }
 // CTA-pair GEMM; maps.b must be the box-128 weight map, maps.out / maps.resid the epilogue maps of the destination.
-static int launch_gemm2_tc(tvb_handle* h, int epi, const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st, int num_sms) {
+static int launch_gemm2_tc(tvb_handle* h, int epi, const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st, int num_sms, int cat = PC_GEMM) {
     if (p.M % 256 || p.N % 256 || p.K % GEMM_BK || p.K1 % GEMM_BK) return fail(TVB_ERR_INVALID, "gemm shape %dx%dx%d not tileable by CTA pairs", p.M, p.N, p.K);
     switch (epi) {
-        case EPI_BF16: return launch_gemm2_tc_t<EPI_BF16>(h, maps, p, st, num_sms);
-        case EPI_GELU_BF16: return launch_gemm2_tc_t<EPI_GELU_BF16>(h, maps, p, st, num_sms);
-        case EPI_RESID_F32: return launch_gemm2_tc_t<EPI_RESID_F32>(h, maps, p, st, num_sms);
-        case EPI_DUAL: return launch_gemm2_tc_t<EPI_DUAL>(h, maps, p, st, num_sms);
-        case EPI_F32: return launch_gemm2_tc_t<EPI_F32>(h, maps, p, st, num_sms);
+        case EPI_BF16: return launch_gemm2_tc_t<EPI_BF16>(h, maps, p, st, num_sms, cat);
+        case EPI_GELU_BF16: return launch_gemm2_tc_t<EPI_GELU_BF16>(h, maps, p, st, num_sms, cat);
+        case EPI_RESID_F32: return launch_gemm2_tc_t<EPI_RESID_F32>(h, maps, p, st, num_sms, cat);
+        case EPI_DUAL: return launch_gemm2_tc_t<EPI_DUAL>(h, maps, p, st, num_sms, cat);
+        case EPI_F32: return launch_gemm2_tc_t<EPI_F32>(h, maps, p, st, num_sms, cat);
+        case EPI_RESID_LN: return launch_gemm2_tc_t<EPI_RESID_LN>(h, maps, p, st, num_sms, cat);
     }
     return fail(TVB_ERR_INVALID, "unknown epilogue %d", epi);
 }
 
 enum LinEpi { LE_PLAIN, LE_GELU, LE_RESID, LE_DUAL };
+// LayerNorm whose fp32 result is not materialised: rows of `x` with per-row (mean, rstd) in `stats` and the norm's affine.
+struct LnRef {
+    const float* x = nullptr;
+    const float2* stats = nullptr;
+    const float *g = nullptr, *b = nullptr;
+};
+static const CUtensorMap& f32_map(tvb_handle* h, const float* ptr) {
+    return ptr == h->xpre ? h->tm_xpre : ptr == h->xalt ? h->tm_xalt : h->tm_hres;
+}
 // y = [a | a2] W^T + b with the epilogue the call site needs, in the active precision.
 //   LE_PLAIN: -> out (Act)          LE_GELU: -> gelu -> out (Act)
-//   LE_RESID: -> + resid -> out_f32 LE_DUAL: -> out_f32 and out (Act)
+//   LE_RESID: -> + resid -> out_f32 (resid = fp32 rows, or LayerNorm(ln->x) re-normalised in the epilogue when ln != nullptr)
+//   LE_DUAL:  -> out_f32 and out (Act)
 static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, LinEpi epi, Act* out, const float* resid, float* out_f32,
-                  cudaStream_t st) {
+                  cudaStream_t st, int cat = PC_GEMM, const LnRef* ln = nullptr) {
     const int Mp = h->L.Mp;
     if (h->precision == TVB_PRECISION_BF16) {
         GemmParams p{};
         p.M = Mp; p.N = lin.N; p.K = lin.K; p.K1 = a2 ? a.C : lin.K;
-        p.bias = lin.bias; p.resid = resid; p.out_f32 = out_f32; p.out_bf16 = out ? out->b16 : nullptr; p.ld_out = lin.N;
-        const int e = epi == LE_PLAIN ? EPI_BF16 : epi == LE_GELU ? EPI_GELU_BF16 : epi == LE_RESID ? EPI_RESID_F32 : EPI_DUAL;
+        p.bias = lin.bias_tc; p.resid = ln ? ln->x : resid; p.out_f32 = out_f32; p.out_bf16 = out ? out->b16 : nullptr; p.ld_out = lin.N;
+        if (ln) { p.ln_stats = ln->stats; p.ln_g = ln->g; p.ln_b = ln->b; }
+        const int e = epi == LE_PLAIN ? EPI_BF16 : epi == LE_GELU ? EPI_GELU_BF16 : epi == LE_RESID ? (ln ? EPI_RESID_LN : EPI_RESID_F32) : EPI_DUAL;
         if (h->opt_gemm_2cta) {
             Gemm2Maps maps;
             maps.a = a.tm; maps.a2 = a2 ? a2->tm : a.tm; maps.b = lin.tm2;
             if (epi == LE_PLAIN || epi == LE_GELU) maps.out = out->tm_out;
-            else maps.out = (out_f32 == h->xpre) ? h->tm_xpre : h->tm_hres;
-            maps.resid = (resid == h->xpre) ? h->tm_xpre : h->tm_hres;
-            return launch_gemm2_tc(h, e, maps, p, st, h->num_sms);
+            else maps.out = f32_map(h, out_f32);
+            maps.resid = f32_map(h, p.resid);
+            return launch_gemm2_tc(h, e, maps, p, st, h->num_sms, cat);
         }
-        return launch_gemm_tc(h, e, a.tm, a2 ? a2->tm : a.tm, lin.tm, p, st, h->num_sms);
+        return launch_gemm_tc(h, e, a.tm, a2 ? a2->tm : a.tm, lin.tm, p, st, h->num_sms, cat);
     }
+    if (ln) return fail(TVB_ERR_STATE, "internal: fused LayerNorm residual is a bf16-path feature");
     SgemmParams p{};
     p.M = Mp; p.N = lin.N; p.K = lin.K; p.K1 = a2 ? a.C : lin.K;
     p.A = a.f32; p.lda = a.C; p.A2 = a2 ? a2->f32 : a.f32; p.lda2 = a2 ? a2->C : a.C;
@@ -721,13 +767,15 @@ static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, Li
     return TVB_OK;
 }
 
-static int layernorm(tvb_handle* h, const float* x, float* y, Act* yb, const float* g, const float* b, cudaStream_t st) {
+// y (fp32, may be nullptr when stats != nullptr) and yb (operand copy in the active precision) = LayerNorm(x); eps 1e-5.
+static int layernorm(tvb_handle* h, const float* x, float* y, Act* yb, const float* g, const float* b, cudaStream_t st,
+                     float2* stats = nullptr) {
     const int Mp = h->L.Mp, H = h->cfg.hidden_size;
     ProfScope ps(h, st, PC_NORM);
     if (h->precision == TVB_PRECISION_BF16)
-        k_layernorm<bf16><<<(Mp + 7) / 8, 256, 0, st>>>(x, y, yb ? yb->b16 : nullptr, g, b, h->L.row_seq, Mp, H, 1e-5f);
+        k_layernorm<bf16><<<(Mp + 7) / 8, 256, 0, st>>>(x, y, yb ? yb->b16 : nullptr, g, b, h->L.row_seq, Mp, H, 1e-5f, stats);
     else
-        k_layernorm<float><<<(Mp + 7) / 8, 256, 0, st>>>(x, y, yb ? yb->f32 : nullptr, g, b, h->L.row_seq, Mp, H, 1e-5f);
+        k_layernorm<float><<<(Mp + 7) / 8, 256, 0, st>>>(x, y, yb ? yb->f32 : nullptr, g, b, h->L.row_seq, Mp, H, 1e-5f, stats);
     h->launches++;
     CKL();
     return TVB_OK;
@@ -736,14 +784,17 @@ static int layernorm(tvb_handle* h, const float* x, float* y, Act* yb, const flo
 static int attention(tvb_handle* h, cudaStream_t st) {
     const int H = h->cfg.hidden_size, nh = h->cfg.num_attention_heads;
     ProfScope ps(h, st, PC_ATTN);
-    if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc) {
-        CK(launch_attn_tc_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_ptmem != 0, st));
+    // bf16 path: q carries head_dim^-0.5 * log2(e) (tvb_finalize_weights), so tensor-core scores are already in the log2 domain
+    if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 4) {
+        CK(launch_attn4_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_poly, st));
+    } else if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc) {
+        CK(launch_attn_tc_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_ptmem != 0, 1.0f, st));
     } else if (h->precision == TVB_PRECISION_BF16) {
         dim3 grid(h->n_work16, nh);
-        k_attn_simt<bf16><<<grid, 128, 0, st>>>(h->qkv.b16, h->ctx.b16, h->L, H, h->slopes, h->d_work16);
+        k_attn_simt<bf16><<<grid, 128, 0, st>>>(h->qkv.b16, h->ctx.b16, h->L, H, h->slopes, h->d_work16, 0.6931471805599453f);
     } else {
         dim3 grid(h->n_work16, nh);
-        k_attn_simt<float><<<grid, 128, 0, st>>>(h->qkv.f32, h->ctx.f32, h->L, H, h->slopes, h->d_work16);
+        k_attn_simt<float><<<grid, 128, 0, st>>>(h->qkv.f32, h->ctx.f32, h->L, H, h->slopes, h->d_work16, 1.0f);
     }
     h->launches++;
     CKL();
@@ -813,7 +864,18 @@ static int run_estimator(tvb_handle* h, const float* y, const float* t_seq_dev, 
     h->launches++;
     CKL();
     for (int i = 0; i < c.convpos_depth; ++i) TRY(posconv(h, i, i == c.convpos_depth - 1, st));
-    TRY(layernorm(h, h->xpre, h->hres, &h->slots[0], h->ln0_g, h->ln0_b, st));
+    // ln_fuse (bf16 path): the fp32 post-LN stream is never written.  Each LayerNorm emits the bf16 GEMM operand and per-row
+    // (mean, rstd); the residual GEMM that needs LayerNorm(x) in fp32 re-normalises x in its epilogue.  The pre-norm sums
+    // ping-pong between xpre and xalt: O-proj reads xpre / writes xalt, FFN-out reads xalt / writes xpre.
+    const bool fuse = bf && h->opt_ln_fuse;
+    LnRef cur_ln;                      // LayerNorm that produced the current layer input (valid when fuse && !plain_resid)
+    bool plain_resid = !fuse;          // the current layer input exists as fp32 rows in hres
+    if (fuse) {
+        TRY(layernorm(h, h->xpre, nullptr, &h->slots[0], h->ln0_g, h->ln0_b, st, h->statsA));
+        cur_ln.x = h->xpre; cur_ln.stats = h->statsA; cur_ln.g = h->ln0_g; cur_ln.b = h->ln0_b;
+    } else {
+        TRY(layernorm(h, h->xpre, h->hres, &h->slots[0], h->ln0_g, h->ln0_b, st));
+    }
 
     int sp = 1;                       // skip stack pointer: slots[0..sp) are live
     const Act* cur = &h->slots[0];    // bf16/fp32 copy of the current layer input
@@ -821,18 +883,36 @@ static int run_estimator(tvb_handle* h, const float* y, const float* t_seq_dev, 
         const LayerW& lw = h->layers[l];
         if (l >= nl / 2) {            // U-Net merge: Linear(2H -> H)([h ; skip]) as a two-operand split-K GEMM (networks.py:361-363)
             const Act* skip = &h->slots[--sp];
-            TRY(linear(h, h->skip[l - nl / 2], *cur, skip, LE_DUAL, &h->hbB, nullptr, h->hres, st));
+            TRY(linear(h, h->skip[l - nl / 2], *cur, skip, LE_DUAL, &h->hbB, nullptr, h->hres, st, PC_GEMM_SKIP));
             cur = &h->hbB;
+            plain_resid = true;
         }
-        TRY(linear(h, lw.qkv, *cur, nullptr, LE_PLAIN, &h->qkv, nullptr, nullptr, st));
+        TRY(linear(h, lw.qkv, *cur, nullptr, LE_PLAIN, &h->qkv, nullptr, nullptr, st, PC_GEMM_QKV));
         TRY(attention(h, st));
-        TRY(linear(h, lw.o, h->ctx, nullptr, LE_RESID, nullptr, h->hres, h->xpre, st));
-        TRY(layernorm(h, h->xpre, h->hres, &h->hbB, lw.ln1_g, lw.ln1_b, st));
-        TRY(linear(h, lw.f1, h->hbB, nullptr, LE_GELU, &h->mid, nullptr, nullptr, st));
-        TRY(linear(h, lw.f2, h->mid, nullptr, LE_RESID, nullptr, h->hres, h->xpre, st));
-        Act* dst = (l < nl / 2 - 1) ? &h->slots[sp++] : &h->hbA;
-        TRY(layernorm(h, h->xpre, h->hres, dst, lw.ln2_g, lw.ln2_b, st));
-        cur = dst;
+        const bool last = (l == nl - 1);
+        if (fuse) {
+            // x1 = attn + (layer input) -> xalt ; LN1 -> hbB + statsB
+            TRY(linear(h, lw.o, h->ctx, nullptr, LE_RESID, nullptr, h->hres, h->xalt, st, PC_GEMM_O, plain_resid ? nullptr : &cur_ln));
+            TRY(layernorm(h, h->xalt, nullptr, &h->hbB, lw.ln1_g, lw.ln1_b, st, h->statsB));
+            TRY(linear(h, lw.f1, h->hbB, nullptr, LE_GELU, &h->mid, nullptr, nullptr, st, PC_GEMM_F1));
+            LnRef ln1;
+            ln1.x = h->xalt; ln1.stats = h->statsB; ln1.g = lw.ln1_g; ln1.b = lw.ln1_b;
+            TRY(linear(h, lw.f2, h->mid, nullptr, LE_RESID, nullptr, nullptr, h->xpre, st, PC_GEMM_F2, &ln1));
+            Act* dst = (l < nl / 2 - 1) ? &h->slots[sp++] : &h->hbA;
+            // the last layer's output feeds the fp32 output projection: materialise it
+            TRY(layernorm(h, h->xpre, last ? h->hres : nullptr, dst, lw.ln2_g, lw.ln2_b, st, h->statsA));
+            cur_ln.x = h->xpre; cur_ln.stats = h->statsA; cur_ln.g = lw.ln2_g; cur_ln.b = lw.ln2_b;
+            plain_resid = false;
+            cur = dst;
+        } else {
+            TRY(linear(h, lw.o, h->ctx, nullptr, LE_RESID, nullptr, h->hres, h->xpre, st, PC_GEMM_O));
+            TRY(layernorm(h, h->xpre, h->hres, &h->hbB, lw.ln1_g, lw.ln1_b, st));
+            TRY(linear(h, lw.f1, h->hbB, nullptr, LE_GELU, &h->mid, nullptr, nullptr, st, PC_GEMM_F1));
+            TRY(linear(h, lw.f2, h->mid, nullptr, LE_RESID, nullptr, h->hres, h->xpre, st, PC_GEMM_F2));
+            Act* dst = (l < nl / 2 - 1) ? &h->slots[sp++] : &h->hbA;
+            TRY(layernorm(h, h->xpre, h->hres, dst, lw.ln2_g, lw.ln2_b, st));
+            cur = dst;
+        }
     }
     // output projection H -> n_feats on the fp32 residual stream (networks.py:372)
     SgemmParams p{};
@@ -971,4 +1051,38 @@ extern "C" int tvb_debug_gemm_bf16(int device, const void* a_dev, const void* w_
         return launch_gemm2_tc(nullptr, e, maps, p, static_cast<cudaStream_t>(stream), prop.multiProcessorCount);
     }
     return launch_gemm_tc(nullptr, epilogue, tmA, tmA, tmB, p, static_cast<cudaStream_t>(stream), prop.multiProcessorCount);
+}
+
+// Kernel-level test hook: the tcgen05 attention kernels alone on caller-provided packed [rows, 3H] bf16 q|k|v
+// (q pre-scaled by head_dim^-0.5 * log2(e)); sequences occupy rows [seq_start[s], seq_start[s] + seq_len[s]).
+extern "C" int tvb_debug_attention(int device, const void* qkv_dev, void* ctx_dev, const int32_t* seq_start_host, const int32_t* seq_len_host,
+                                   int32_t nseq, int32_t rows, int32_t H, int32_t nheads, const float* slopes_dev, int32_t version,
+                                   int32_t poly, void* stream) {
+    if (!qkv_dev || !ctx_dev || !seq_start_host || !seq_len_host || !slopes_dev || nseq <= 0) return fail(TVB_ERR_INVALID, "bad argument");
+    if (H != nheads * 64) return fail(TVB_ERR_INVALID, "head_dim must be 64");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(TVB_ERR_INVALID, "sm_100a device required");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::vector<int4> work;
+    for (int s = 0; s < nseq; ++s) {
+        if (seq_len_host[s] <= 0 || seq_start_host[s] < 0 || seq_start_host[s] + seq_len_host[s] > rows) return fail(TVB_ERR_INVALID, "bad sequence %d", s);
+        for (int q0 = 0; q0 < seq_len_host[s]; q0 += ATT_BQ) work.push_back(make_int4(s, q0, seq_start_host[s], seq_len_host[s]));
+    }
+    int4* d_work = nullptr;
+    CK(cudaMalloc(&d_work, work.size() * sizeof(int4)));
+    CK(cudaMemcpyAsync(d_work, work.data(), work.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+    CUtensorMap tm;
+    int rc = make_tmap(&tm, qkv_dev, rows, 3 * H, 3 * H, 128);
+    if (rc == TVB_OK) {
+        cudaError_t e;
+        if (version == 4) e = launch_attn4_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, st);
+        else e = launch_attn_tc_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), version != 2, 1.0f, st);
+        if (e != cudaSuccess) rc = fail(TVB_ERR_CUDA, "attention launch: %s", cudaGetErrorString(e));
+    }
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(d_work);
+    if (rc == TVB_OK && e2 != cudaSuccess) return fail(TVB_ERR_CUDA, "attention kernel: %s", cudaGetErrorString(e2));
+    return rc;
 }

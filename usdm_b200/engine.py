@@ -43,6 +43,8 @@ _SIGNATURES = {
     "tvb_kernel_launches": (C.c_int64, [_P]),
     "tvb_device_bytes": (C.c_int64, [_P]),
     "tvb_debug_gemm_bf16": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "tvb_debug_attention": (C.c_int, [C.c_int, _P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, _P, C.c_int32, C.c_int32, _P]),
     "tvb_last_error": (C.c_char_p, []),
     "tvb_version": (C.c_char_p, []),
 }

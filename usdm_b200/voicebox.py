@@ -306,16 +306,17 @@ class Voicebox(nn.Module, PyTorchModelHubMixin):
     def kernel_launches(self) -> int:
         return 0 if self._handle is None else int(E.load_library().tvb_kernel_launches(self._handle))
 
-    PROFILE_CATEGORIES = ("gemm", "attention", "posconv", "layernorm", "frame_proj", "output")
+    PROFILE_CATEGORIES = ("gemm", "attention", "posconv", "layernorm", "frame_proj", "output", None, None,
+                          "gemm_qkv", "gemm_attn_out", "gemm_ffn_in", "gemm_ffn_out", "gemm_skip", None, None, None)
 
     def read_profile(self):
         """{category: (milliseconds, launches)} accumulated since set_option("profile", 1) / the last read."""
         if self._handle is None:
             return {}
-        ms = (C.c_double * 8)()
-        n = (C.c_int64 * 8)()
+        ms = (C.c_double * 16)()
+        n = (C.c_int64 * 16)()
         E.check(E.load_library().tvb_profile_read(self._handle, ms, n))
-        return {name: (ms[i], int(n[i])) for i, name in enumerate(self.PROFILE_CATEGORIES)}
+        return {name: (ms[i], int(n[i])) for i, name in enumerate(self.PROFILE_CATEGORIES) if name is not None}
 
     def device_bytes(self) -> int:
         return 0 if self._handle is None else int(E.load_library().tvb_device_bytes(self._handle))
