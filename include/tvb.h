@@ -71,7 +71,8 @@ int tvb_set_precision(tvb_handle* h, int32_t precision);
 int tvb_get_precision(const tvb_handle* h);
 /* Ablation / cross-check switches of the bf16 path: "attn_tc" and "conv_tc" (1 = tcgen05 kernel, default;
  * 0 = the CUDA-core kernel of the same op; both are GPU kernels of this library, there is no CPU path),
- * "gemm_2cta" (1 = CTA-pair tcgen05 GEMM, default; 0 = single-CTA tcgen05 GEMM), "attn_v" (4 = attn4_tc.cuh, default;
+ * "gemm_2cta" (1 = CTA-pair tcgen05 GEMM, default; 0 = single-CTA tcgen05 GEMM), "gemm_mc" (1 = two CTA pairs per cluster
+ * sharing the W tile by TMA multicast, default; 0 = independent pairs), "attn_v" (4 = attn4_tc.cuh, default;
  * 3 = attn_tc.cuh), "attn_poly" (attention v4: 0 = every exp2 on MUFU; 2/3/4 = one element pair in n on the FMA-pipe
  * polynomial), "ln_fuse" (1 = LayerNorm re-applied in the residual GEMM epilogue instead of materialising the fp32
  * stream, default; 0 = separate fp32 LayerNorm output), and "profile" (see tvb_profile_read). */
@@ -122,7 +123,8 @@ int64_t tvb_device_bytes(const tvb_handle* h);
 /* Kernel-level test hooks (used by tests/ only): a single tcgen05 GEMM  C = A * W^T + bias with a chosen epilogue.
  * a_dev bf16 [M,K], w_dev bf16 [N,K], bias_dev fp32 [N] or NULL, resid_dev fp32 [M,N] or NULL,
  * out_f32_dev fp32 [M,N] or NULL, out_bf16_dev bf16 [M,N] or NULL.  epilogue: 0 bf16, 1 gelu->bf16, 2 +resid->f32,
- * 3 f32+bf16, 4 f32; OR 0x100 to run the CTA-pair (cta_group::2) kernel (then M % 256 == 0).
+ * 3 f32+bf16, 4 f32; OR 0x100 to run the CTA-pair (cta_group::2) kernel (then M % 256 == 0), OR 0x200 for the
+ * cluster-of-4 multicast kernel (then M % 512 == 0).
  * M % 128 == 0, N % 256 == 0, K % 64 == 0. */
 int tvb_debug_gemm_bf16(int device, const void* a_dev, const void* w_dev, const float* bias_dev, const float* resid_dev,
                         float* out_f32_dev, void* out_bf16_dev, int32_t M, int32_t N, int32_t K, int32_t epilogue,

@@ -62,3 +62,31 @@ def test_gemm_epilogues(epi, pair):
         assert (ob.float() - ref.to(torch.bfloat16).float()).abs().max().item() < 0.05
     err = (got - want).abs().max().item()
     assert err < 0.03, f"epilogue {epi}: max abs err {err}"
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("M,N,K", [(512, 256, 64), (512, 512, 128), (1024, 256, 512), (1024, 1024, 1024),
+                                   (1536, 3072, 1024), (512, 1024, 4096), (148 * 128 * 2 + 512, 1024, 1024)])
+def test_gemm_cluster4_multicast_f32_epilogue(M, N, K):
+    """Cluster of two CTA pairs sharing the W tile by TMA multicast (gemm4_tc_kernel)."""
+    ref, _, of, _ = _run(M, N, K, 4 | 0x200)
+    err = (of - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("epi", [0, 1, 2, 3])
+def test_gemm_cluster4_epilogues(epi):
+    M, N, K = 1024, 1024, 1024
+    ref, resid, of, ob = _run(M, N, K, epi | 0x200, seed=epi + 11)
+    if epi == 0:
+        want = ref.to(torch.bfloat16).float(); got = ob.float()
+    elif epi == 1:
+        want = torch.nn.functional.gelu(ref).to(torch.bfloat16).float(); got = ob.float()
+    elif epi == 2:
+        want = ref + resid; got = of
+    else:
+        want = ref; got = of
+        assert (ob.float() - ref.to(torch.bfloat16).float()).abs().max().item() < 0.05
+    err = (got - want).abs().max().item()
+    assert err < 0.03, f"epilogue {epi}: max abs err {err}"

@@ -12,8 +12,8 @@
 //     key-side tile (jrel = 0..127 exact in bf16, sigma split into three bf16 terms), i.e. adds -+sigma*(j - k0) exactly;
 //     the remaining per-row constant -+sigma*(i - k0) is folded into the exponent offset.  Only the single diagonal block
 //     of each half evaluates |i - j| in registers.  Per element the softmax is: max, add, exp2, add, convert.
-//  3. Lazy rescale: the reference maximum of a row only moves when the block maximum exceeds it by more than 2^8
-//     (P stays <= 256, exact enough in bf16/fp32), so the O read-modify-write is rare.
+//  3. Lazy rescale: the reference maximum of a row only moves when the block maximum exceeds it by more than 2^16
+//     (P stays <= 65536: harmless in bf16 / fp32), so the O read-modify-write is rare.
 //  4. Optional exp2 offload: every POLY-th element pair is exponentiated on the FMA pipe (round-to-nearest split +
 //     degree-3 polynomial, max rel. error 7.5e-5, far below the bf16 rounding of P) instead of MUFU.EX2.
 //
@@ -31,7 +31,7 @@ constexpr int A4_SMEM_KV = 2 * ATT_TILE_BYTES;                                 /
 constexpr int A4_SMEM_EXT = A4_SMEM_KV + A4_KV_STAGES * 2 * ATT_TILE_BYTES;    // 16 KB: bias operand tile
 constexpr int A4_SMEM_BAR = A4_SMEM_EXT + ATT_TILE_BYTES;
 constexpr int A4_SMEM_BYTES = A4_SMEM_BAR + 256;
-constexpr float A4_RESCALE_LOG2 = 8.0f;
+constexpr float A4_RESCALE_LOG2 = 16.0f;
 
 // 2^x for x <= 0 on the FMA pipe, two elements at a time (Cody-Waite split at round-to-nearest, degree-3 minimax on [-.5,.5]).
 __device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
@@ -73,8 +73,9 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
     uint64_t* kv_full = bars + 1;                       // [4]
     uint64_t* kv_empty = kv_full + A4_KV_STAGES;        // [4]
     uint64_t* s_full = kv_empty + A4_KV_STAGES;         // [3] per S buffer
-    uint64_t* p_ready = s_full + 3;                     // [2] per half
-    uint64_t* pv_done = p_ready + 2;                    // [2] per half
+    uint64_t* p_ready = s_full + 3;                     // [3] per S buffer (a warp may run one block ahead of its half: per-half
+                                                        //     counting would mix the arrivals of two blocks)
+    uint64_t* pv_done = p_ready + 3;                    // [2] per half
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,8 +93,8 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
     if (warp_idx == 1 && lane == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < A4_KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        for (int s = 0; s < 3; ++s) mbar_init(&s_full[s], 1);
-        for (int t = 0; t < 2; ++t) { mbar_init(&p_ready[t], 128); mbar_init(&pv_done[t], 1); }
+        for (int s = 0; s < 3; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_ready[s], 128); }
+        for (int t = 0; t < 2; ++t) mbar_init(&pv_done[t], 1);
         fence_barrier_init();
     }
     if (warp_idx == 2) tmem_alloc<512>(tmem_slot);
@@ -176,7 +177,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                 const int half = two ? (n & 1) : 0;
                 const int j = two ? (n >> 1) : n;
                 const int slot = j % A4_KV_STAGES;
-                mbar_wait(&p_ready[half], j & 1);
+                mbar_wait(&p_ready[n % 3], (n / 3) & 1);
                 tc_fence_after();
                 const uint32_t sV = smem_u32(smem + A4_SMEM_KV + slot * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES);
                 const uint32_t tP = tmem_base + (n % 3) * 128;
@@ -210,55 +211,131 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
             const int i = qt + r;                           // query position in the sequence
             const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
             const uint32_t tmem_O = tmem_base + 384 + half * 64 + lane_off;
+            const float a0d = -slope2 * static_cast<float>(r);   // diagonal block: -sigma |r - e| = min(A, -A), A = sigma e - sigma r
             float m_ref = 0.f, l_run = 0.f;
             for (int j = 0; j < nkb; ++j) {
                 const int n = two ? 2 * j + half : j;
                 const int k0 = j * ATT_BK;
-                const uint32_t tmem_S = tmem_base + (n % 3) * 128 + lane_off;
-                mbar_wait(&s_full[n % 3], (n / 3) & 1);
+                const int buf = n % 3;
+                const uint32_t tmem_S = tmem_base + buf * 128 + lane_off;
+                const bool diag = (j == jd);
+                const bool partial = (k0 + ATT_BK > len);
+                // additive term of this block: per-row constant (off-diagonal; the j-dependent part came out of the MMA) or none
+                const float c_row = diag ? 0.f : -slope2 * fabsf(static_cast<float>(i - k0));
+                mbar_wait(&s_full[buf], (n / 3) & 1);
                 tc_fence_after();
+                // s[0,64): bf16 pairs of P (output); fast path: s[64,96) / s[96,128) double-buffer 32-column chunks of S
                 uint32_t s[128];
+                uint32_t(&ca)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
+                uint32_t(&cb)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
+                float lsum = 0.f;
+                bool need_full = (j == 0);
+                if (j > 0) {
+                    // ---- fast path: exponentiate against the standing reference maximum while the next chunk streams out of
+                    // TMEM (the TMEM read port and MUFU are both near saturation: neither may wait for the other); the block
+                    // maximum is only checked afterwards.
+                    const float off = c_row - m_ref;
+                    const uint64_t off2 = pack2f(off, off);
+                    uint64_t acc2 = pack2f(0.f, 0.f);
+                    float mxa = -INFINITY, mxb = -INFINITY;
+                    auto proc = [&](uint32_t(&cur)[32], const int c) {
+                        if (diag) {
+                            const float s0raw = __uint_as_float(cur[0]);
+                            float a0v = a0d;
+                            asm volatile("" : "+f"(a0v));                   // keep the 128 bias values from being hoisted out of the block loop
 #pragma unroll
-                for (int c = 0; c < 4; ++c) tmem_ld_32x32(tmem_S + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
-                tmem_ld_wait();
-                // ---- additive term: row constant (off-diagonal) or |i - j| in registers (diagonal block)
-                float c_row;
-                if (j == jd) {
-                    c_row = 0.f;
-                    const float s0raw = __uint_as_float(s[0]);
-                    const float a0 = -slope2 * static_cast<float>(r);       // -sigma |r - e| = min(A, -A), A = sigma e - sigma r
+                            for (int e = 0; e < 32; ++e) {
+                                const float a = fmaf(slope2, static_cast<float>(c * 32 + e), a0v);
+                                cur[e] = __float_as_uint(__uint_as_float(cur[e]) + fminf(a, -a));
+                            }
+                            if (c == 0 && k0 == 0) cur[0] = __float_as_uint(s0raw);     // key 0 (time token): no distance penalty
+                        } else if (c == 0 && k0 == 0) {
+                            cur[0] = __float_as_uint(__uint_as_float(cur[0]) - c_row);
+                        }
+                        if (partial) {
 #pragma unroll
-                    for (int e = 0; e < 128; ++e) {
-                        const float a = fmaf(slope2, static_cast<float>(e), a0);
-                        s[e] = __float_as_uint(__uint_as_float(s[e]) + fminf(a, -a));
+                            for (int e = 0; e < 32; ++e)
+                                if (k0 + c * 32 + e >= len) cur[e] = __float_as_uint(-INFINITY);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) {
+                            const float x0 = __uint_as_float(cur[2 * u]), x1 = __uint_as_float(cur[2 * u + 1]);
+                            if (u & 1) mxb = fmaxf(mxb, fmaxf(x0, x1));
+                            else mxa = fmaxf(mxa, fmaxf(x0, x1));
+                            const uint64_t x2 = fadd2(pack2f(x0, x1), off2);
+                            uint64_t p2;
+                            if (POLY > 0 && (u % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) {
+                                p2 = exp2_poly2(x2);
+                            } else {
+                                float lo, hi;
+                                unpack2f(x2, lo, hi);
+                                p2 = pack2f(ex2_approx(lo), ex2_approx(hi));
+                            }
+                            acc2 = fadd2(acc2, p2);
+                            float lo, hi;
+                            unpack2f(p2, lo, hi);
+                            s[c * 16 + u] = pack_bf16x2(lo, hi);
+                        }
+                    };
+                    tmem_ld_32x32(tmem_S, ca);
+                    tmem_ld_wait_dep(ca);
+                    tmem_ld_32x32(tmem_S + 32, cb);
+                    proc(ca, 0);
+                    tmem_ld_wait_dep(cb);
+                    tmem_ld_32x32(tmem_S + 64, ca);
+                    proc(cb, 1);
+                    tmem_ld_wait_dep(ca);
+                    tmem_ld_32x32(tmem_S + 96, cb);
+                    proc(ca, 2);
+                    tmem_ld_wait_dep(cb);
+                    proc(cb, 3);
+                    float a0, a1;
+                    unpack2f(acc2, a0, a1);
+                    lsum = a0 + a1;
+                    const float m_blk = fmaxf(mxa, mxb) + c_row;          // block maximum in the true (biased) domain
+                    // P must stay <= 2^16: if any row of the warp outgrew its reference, redo the block the careful way
+                    need_full = __any_sync(0xffffffffu, m_blk > m_ref + A4_RESCALE_LOG2);
+                }
+                bool pv_seen = false;
+                if (need_full) {
+                    // ---- full path (first block, or a reference maximum has to move): whole row in registers, maximum first
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) tmem_ld_32x32(tmem_S + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+                    tmem_ld_wait();
+                    if (diag) {
+                        const float s0raw = __uint_as_float(s[0]);
+                        float a0v = a0d;
+                        asm volatile("" : "+f"(a0v));
+#pragma unroll
+                        for (int e = 0; e < 128; ++e) {
+                            const float a = fmaf(slope2, static_cast<float>(e), a0v);
+                            s[e] = __float_as_uint(__uint_as_float(s[e]) + fminf(a, -a));
+                        }
+                        if (k0 == 0) s[0] = __float_as_uint(s0raw);
+                    } else if (k0 == 0) {
+                        s[0] = __float_as_uint(__uint_as_float(s[0]) - c_row);
                     }
-                    if (k0 == 0) s[0] = __float_as_uint(s0raw);           // key 0 (time token) carries no distance penalty
-                } else {
-                    c_row = -slope2 * fabsf(static_cast<float>(i - k0));
-                    if (k0 == 0) s[0] = __float_as_uint(__uint_as_float(s[0]) - c_row);
-                }
-                if (k0 + ATT_BK > len) {
+                    if (partial) {
 #pragma unroll
-                    for (int e = 0; e < 128; ++e)
-                        if (k0 + e >= len) s[e] = __float_as_uint(-INFINITY);
-                }
-                float mx0 = -INFINITY, mx1 = -INFINITY;
+                        for (int e = 0; e < 128; ++e)
+                            if (k0 + e >= len) s[e] = __float_as_uint(-INFINITY);
+                    }
+                    float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-                for (int e = 0; e < 128; e += 4) {
-                    mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s[e]), __uint_as_float(s[e + 1])));
-                    mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s[e + 2]), __uint_as_float(s[e + 3])));
-                }
-                const float m_blk = fmaxf(mx0, mx1) + c_row;              // block maximum in the true (biased) domain
-                if (j == 0) {
-                    m_ref = m_blk;
-                } else {
-                    const bool grow = m_blk > m_ref + A4_RESCALE_LOG2;
-                    if (__any_sync(0xffffffffu, grow)) {
-                        const float m_new = grow ? m_blk : m_ref;
-                        const float alpha = ex2_approx(m_ref - m_new);
+                    for (int e = 0; e < 128; e += 4) {
+                        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s[e]), __uint_as_float(s[e + 1])));
+                        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s[e + 2]), __uint_as_float(s[e + 3])));
+                    }
+                    const float m_blk = fmaxf(mx0, mx1) + c_row;
+                    if (j == 0) {
+                        m_ref = m_blk;
+                    } else {
+                        const float m_new = (m_blk > m_ref + A4_RESCALE_LOG2) ? m_blk : m_ref;
+                        const float alpha = ex2_approx(m_ref - m_new);    // 1 for rows whose reference stays
                         m_ref = m_new;
                         l_run *= alpha;
                         mbar_wait(&pv_done[half], (j - 1) & 1);          // O is only stable once the previous PV has retired
+                        pv_seen = true;
                         tc_fence_after();
 #pragma unroll
                         for (int c = 0; c < ATT_D / 16; ++c) {
@@ -271,35 +348,33 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                         }
                         tmem_st_wait();
                     }
-                }
-                // ---- P = exp2(s + c_row - m_ref), row sum, bf16 pairs back into the first 64 columns of this S buffer
-                const float off = c_row - m_ref;
-                const uint64_t off2 = pack2f(off, off);
-                uint64_t acc2 = pack2f(0.f, 0.f);
+                    const float off = c_row - m_ref;
+                    const uint64_t off2 = pack2f(off, off);
+                    uint64_t acc2 = pack2f(0.f, 0.f);
 #pragma unroll
-                for (int u = 0; u < 64; ++u) {
-                    const uint64_t x2 = fadd2(pack2f(__uint_as_float(s[2 * u]), __uint_as_float(s[2 * u + 1])), off2);
-                    uint64_t p2;
-                    if (POLY > 0 && (u % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) {
-                        p2 = exp2_poly2(x2);
-                    } else {
+                    for (int u = 0; u < 64; ++u) {
+                        const uint64_t x2 = fadd2(pack2f(__uint_as_float(s[2 * u]), __uint_as_float(s[2 * u + 1])), off2);
                         float lo, hi;
                         unpack2f(x2, lo, hi);
-                        p2 = pack2f(ex2_approx(lo), ex2_approx(hi));
+                        lo = ex2_approx(lo);
+                        hi = ex2_approx(hi);
+                        acc2 = fadd2(acc2, pack2f(lo, hi));
+                        s[u] = pack_bf16x2(lo, hi);
                     }
-                    acc2 = fadd2(acc2, p2);
-                    float lo, hi;
-                    unpack2f(p2, lo, hi);
-                    s[u] = pack_bf16x2(lo, hi);
+                    float a0, a1;
+                    unpack2f(acc2, a0, a1);
+                    lsum = a0 + a1;
                 }
+                // Every thread observes every phase of pv_done exactly once and BEFORE it lets PV(j) start (parity waits are only
+                // unambiguous within one phase).  PV(j-1) was issued a whole block ago, so this does not stall.
+                if (j > 0 && !pv_seen) mbar_wait(&pv_done[half], (j - 1) & 1);
+                l_run += lsum;
+                // ---- bf16 pairs of P into the first 64 columns of this S buffer (A operand of the PV MMA)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) tmem_st_32x16(tmem_S + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&s[c * 16]));
                 tmem_st_wait();
-                float a0, a1;
-                unpack2f(acc2, a0, a1);
-                l_run += a0 + a1;
                 tc_fence_before();
-                mbar_arrive(&p_ready[half]);
+                mbar_arrive(&p_ready[buf]);
             }
             // epilogue: O / l -> ctx (bf16), only rows that belong to the sequence
             mbar_wait(&pv_done[half], (nkb - 1) & 1);

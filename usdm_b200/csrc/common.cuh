@@ -151,6 +151,17 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorM
         "l"(reinterpret_cast<uint64_t>(map)), "r"(mbar), "r"(c_inner), "r"(c_outer)
         : "memory");
 }
+// Same, multicast: the box lands at the same smem offset in every CTA of `cta_mask`, and in each of them the bytes are credited
+// to the barrier (same offset) of that CTA's pair leader.
+__device__ __forceinline__ void tma_load_2d_2cta_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c_inner,
+                                                    int32_t c_outer, uint16_t cta_mask) {
+    const uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(mbar), "r"(c_inner), "r"(c_outer), "h"(cta_mask)
+        : "memory");
+}
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_result) {   // one full warp in EACH CTA of the pair
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(kCols)
@@ -261,6 +272,17 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Same wait, but the 32 destination registers of the load it completes are tied to it as in/out operands, so that no use of
+// them can be scheduled above the wait when other work is interleaved between the load and the wait.
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                   "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                   "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 }  // namespace tvb

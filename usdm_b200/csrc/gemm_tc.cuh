@@ -248,9 +248,14 @@ struct Gemm2Maps {
     CUtensorMap resid;        // fp32 [M,N] box 32x32 (EPI_RESID_F32)
 };
 
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
-gemm2_tc_kernel(const __grid_constant__ Gemm2Maps tm, const GemmParams p) {
+// NP = CTA pairs per cluster.  NP == 1: the kernel described above.  NP == 2 (cluster of 4): the two pairs work on vertically
+// adjacent 256-row tiles of the SAME 256 W rows; every CTA fetches only 64 of the 128 W rows it needs and TMA-multicasts them to
+// the CTA of the other pair that needs the same rows, so a k-block costs 24 KB of L2->SM traffic per CTA instead of 32 KB
+// (measured: the NP == 1 kernel saturates the L2->SM fabric at ~10 TB/s, i.e. ~1.2-1.3 PFLOP/s at 128 FLOP/B, profiles/r01).
+// A stage may be overwritten once BOTH pairs have consumed it: each pair leader's commit arrives on the empty barrier of all
+// four CTAs (barrier count NP).
+template <int EPI, int NP>
+__device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmParams& p) {
     extern __shared__ uint8_t smem_raw[];
     // identical carve-up in both CTAs (the dynamic smem base offset is the same for every CTA of a kernel)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -262,18 +267,21 @@ gemm2_tc_kernel(const __grid_constant__ Gemm2Maps tm, const GemmParams p) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 2 * G2_EPI_WARPS);
 
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t cta = cluster_ctarank();          // 0 = leader
+    const uint32_t crank = cluster_ctarank();
+    const uint32_t cta = crank & 1;                  // position inside the pair, 0 = leader
+    const int pair_id = static_cast<int>(crank >> 1);
     const int tiles_n = p.N / 256;
-    const int num_tiles = (p.M / 256) * tiles_n;
+    const int num_tiles = (p.M / (256 * NP)) * tiles_n;      // cluster tiles: NP vertically adjacent 256 x 256 tiles
     const int num_kb = p.K / GEMM_BK;
-    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int cluster_id = blockIdx.x / (2 * NP), num_clusters = gridDim.x / (2 * NP);
+    auto tile_m0 = [&](int tile) { return ((tile / tiles_n) * NP + pair_id) * 256; };
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tm.a); tma_prefetch_desc(&tm.a2); tma_prefetch_desc(&tm.b); tma_prefetch_desc(&tm.out);
         if (EPI == EPI_RESID_F32 || EPI == EPI_RESID_LN) tma_prefetch_desc(&tm.resid);
     }
     if (warp_idx == 1 && lane == 0) {
-        for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NP); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * G2_EPI_WARPS); }
         for (int s = 0; s < 2 * G2_EPI_WARPS; ++s) mbar_init(&rbar[s], 1);
         fence_barrier_init();
@@ -288,7 +296,7 @@ gemm2_tc_kernel(const __grid_constant__ Gemm2Maps tm, const GemmParams p) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                const int m0 = (tile / tiles_n) * 256 + static_cast<int>(cta) * 128;
+                const int m0 = tile_m0(tile) + static_cast<int>(cta) * 128;
                 const int n0 = (tile % tiles_n) * 256 + static_cast<int>(cta) * 128;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -297,6 +305,11 @@ gemm2_tc_kernel(const __grid_constant__ Gemm2Maps tm, const GemmParams p) {
                     const int k0 = kb * GEMM_BK;
                     if (k0 < p.K1) tma_load_2d_2cta(sa, &tm.a, &full_bar[stage], k0, m0);
                     else           tma_load_2d_2cta(sa, &tm.a2, &full_bar[stage], k0 - p.K1, m0);
+                    if constexpr (NP == 2) {
+                        // 64 of my 128 W rows, delivered to me and to the CTA with my pair position in the other pair
+                        tma_load_2d_2cta_mc(sa + G2_A_BYTES + pair_id * (G2_B_BYTES / 2), &tm.b, &full_bar[stage], k0, n0 + pair_id * 64,
+                                            static_cast<uint16_t>(0x5u << cta));
+                    } else
                     tma_load_2d_2cta(sa + G2_A_BYTES, &tm.b, &full_bar[stage], k0, n0);
                     if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -319,10 +332,10 @@ gemm2_tc_kernel(const __grid_constant__ Gemm2Maps tm, const GemmParams p) {
                     const uint64_t db = make_smem_desc_sw128(sa + G2_A_BYTES, 16, 1024);
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k) umma_ss_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                    umma_commit_2cta(&empty_bar[stage], 3);
+                    umma_commit_2cta(&empty_bar[stage], NP == 2 ? 0xF : 0x3);   // every CTA that writes into these stages
                     if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_2cta(&tfull_bar[as], 3);
+                umma_commit_2cta(&tfull_bar[as], static_cast<uint16_t>(0x3u << (2 * pair_id)));
             }
         }
     } else {
@@ -339,7 +352,7 @@ gemm2_tc_kernel(const __grid_constant__ Gemm2Maps tm, const GemmParams p) {
         const int r7 = lane & 7;
         uint32_t kc = 0;                                          // running chunk counter -> staging buffer / parity
         auto chunk_coords = [&](int tile, int c, int& col, int& row) {
-            row = (tile / tiles_n) * 256 + static_cast<int>(cta) * 128 + quad * 32;
+            row = tile_m0(tile) + static_cast<int>(cta) * 128 + quad * 32;
             col = (tile % tiles_n) * 256 + chalf * 128 + c * kChunkCols;
         };
         if constexpr (kResid) {
@@ -448,7 +461,7 @@ gemm2_tc_kernel(const __grid_constant__ Gemm2Maps tm, const GemmParams p) {
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);   // the leader's MMA thread owns accumulator reuse
+            if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], static_cast<uint32_t>(2 * pair_id));   // the pair leader's MMA thread owns accumulator reuse
         }
         if (lane == 0) tma_store_wait_read<0>();
     }
@@ -459,6 +472,18 @@ gemm2_tc_kernel(const __grid_constant__ Gemm2Maps tm, const GemmParams p) {
         tc_fence_after();
         tmem_dealloc_2cta<512>(tmem_base);
     }
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm2_tc_kernel(const __grid_constant__ Gemm2Maps tm, const GemmParams p) {
+    gemm_pair_body<EPI, 1>(tm, p);
+}
+// Cluster of 4 = two CTA pairs sharing the W tile by TMA multicast; tm.b must be the box-64 weight map; M % 512 == 0.
+template <int EPI>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm4_tc_kernel(const __grid_constant__ Gemm2Maps tm, const GemmParams p) {
+    gemm_pair_body<EPI, 2>(tm, p);
 }
 
 }  // namespace tvb

@@ -98,6 +98,7 @@ struct Lin {                 // one nn.Linear: y = x W^T + b
     int N = 0, K = 0;
     CUtensorMap tm;          // B operand map: [N, K], box 256 x 64 (single-CTA kernel)
     CUtensorMap tm2;         // B operand map: [N, K], box 128 x 64 (CTA-pair kernel: each CTA stages half of the W tile)
+    CUtensorMap tm3;         // B operand map: [N, K], box  64 x 64 (cluster-of-4 kernel: each CTA fetches a quarter and multicasts it)
 };
 struct Act {                 // an activation buffer [Mp, C] in the precision of the active path
     float* f32 = nullptr;
@@ -123,8 +124,9 @@ struct tvb_handle {
     int opt_attn_tc = 1;        // bf16 path: 1 = tcgen05 attention, 0 = CUDA-core attention (ablation / cross-check)
     int opt_conv_tc = 1;        // bf16 path: 1 = tcgen05 positional conv, 0 = CUDA-core conv
     int opt_gemm_2cta = 1;      // bf16 path: 1 = CTA-pair (cta_group::2) GEMM, 0 = single-CTA GEMM
+    int opt_gemm_mc = 1;        // CTA-pair GEMM: 1 = clusters of two pairs sharing the W tile by TMA multicast, 0 = independent pairs
     int opt_attn_ptmem = 1;     // tcgen05 attention v3: 1 = P kept in tensor memory (TS MMA), 0 = P staged through shared memory
-    int opt_attn_v = 3;         // tcgen05 attention kernel generation: 4 = attn4_tc.cuh (default), 3 = attn_tc.cuh
+    int opt_attn_v = 4;         // tcgen05 attention kernel generation: 4 = attn4_tc.cuh (default), 3 = attn_tc.cuh
     int opt_attn_poly = 0;      // attention v4: 0 = every exp2 on MUFU, n = one element pair in n on the FMA-pipe polynomial
     int opt_ln_fuse = 1;        // bf16 path: 1 = LayerNorm writes bf16 + (mean, rstd) only and the residual GEMM epilogue re-normalises
                                 //            the fp32 stream on the fly (EPI_RESID_LN); 0 = LayerNorm materialises the fp32 result
@@ -313,6 +315,7 @@ static int make_lin(tvb_handle* h, Lin* lin, const float* w32, const float* bias
     CKL();
     TRY(make_tmap(&lin->tm, lin->w16, N, K, K, GEMM_BN));
     TRY(make_tmap(&lin->tm2, lin->w16, N, K, K, 128));
+    TRY(make_tmap(&lin->tm3, lin->w16, N, K, K, 64));
     return TVB_OK;
 }
 
@@ -507,6 +510,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     if (!strcmp(name, "attn_tc")) h->opt_attn_tc = value ? 1 : 0;
     else if (!strcmp(name, "conv_tc")) h->opt_conv_tc = value ? 1 : 0;
     else if (!strcmp(name, "gemm_2cta")) h->opt_gemm_2cta = value ? 1 : 0;
+    else if (!strcmp(name, "gemm_mc")) h->opt_gemm_mc = value ? 1 : 0;
     else if (!strcmp(name, "attn_ptmem")) h->opt_attn_ptmem = value ? 1 : 0;
     else if (!strcmp(name, "attn_v")) { if (value != 3 && value != 4) return fail(TVB_ERR_INVALID, "attn_v must be 3 or 4"); h->opt_attn_v = value; }
     else if (!strcmp(name, "attn_poly")) { if (value != 0 && value != 2 && value != 3 && value != 4) return fail(TVB_ERR_INVALID, "attn_poly must be 0, 2, 3 or 4"); h->opt_attn_poly = value; }
@@ -553,7 +557,7 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
     }
     if (o > (1ll << 30)) return fail(TVB_ERR_INVALID, "batch too large");
     const int nhalf = cfg_double ? 2 : 1;
-    const int64_t halign = cfg_double ? 128 : 256;          // Mp must be a multiple of 256 (CTA-pair GEMM tiles)
+    const int64_t halign = cfg_double ? 256 : 512;          // Mp must be a multiple of 512 (two vertically adjacent CTA-pair GEMM tiles per cluster)
     const int half = static_cast<int>((o + halign - 1) / halign * halign);
     const int Mp = half * nhalf;
     const int nseq = B * nhalf;
@@ -706,6 +710,45 @@ static int launch_gemm2_tc_t(tvb_handle* h, const Gemm2Maps& maps, const GemmPar
     CKL();
     return TVB_OK;
 }
+template <int EPI>
+static int launch_gemm4_tc_t(tvb_handle* h, const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st, int cat) {
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+        CK(cudaFuncSetAttribute(gemm4_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(4 * 64);
+        cfg.blockDim = dim3(G2_THREADS);
+        cfg.dynamicSmemBytes = G2_SMEM_BYTES;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        CK(cudaOccupancyMaxActiveClusters(&n, gemm4_tc_kernel<EPI>, &cfg));
+        if (n < 1) return fail(TVB_ERR_CUDA, "no 4-CTA cluster fits on this device");
+        max_clusters = n;
+    }
+    const int tiles = (p.M / 512) * (p.N / 256);
+    const int clusters = tiles < max_clusters ? tiles : max_clusters;
+    ProfScope ps(h, st, cat);
+    gemm4_tc_kernel<EPI><<<4 * clusters, G2_THREADS, G2_SMEM_BYTES, st>>>(maps, p);
+    if (h) h->launches++;
+    CKL();
+    return TVB_OK;
+}
+// Cluster-of-4 multicast GEMM; maps.b must be the box-64 weight map.
+static int launch_gemm4_tc(tvb_handle* h, int epi, const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st, int cat = PC_GEMM) {
+    if (p.M % 512 || p.N % 256 || p.K % GEMM_BK || p.K1 % GEMM_BK) return fail(TVB_ERR_INVALID, "gemm shape %dx%dx%d not tileable by 4-CTA clusters", p.M, p.N, p.K);
+    switch (epi) {
+        case EPI_BF16: return launch_gemm4_tc_t<EPI_BF16>(h, maps, p, st, cat);
+        case EPI_GELU_BF16: return launch_gemm4_tc_t<EPI_GELU_BF16>(h, maps, p, st, cat);
+        case EPI_RESID_F32: return launch_gemm4_tc_t<EPI_RESID_F32>(h, maps, p, st, cat);
+        case EPI_DUAL: return launch_gemm4_tc_t<EPI_DUAL>(h, maps, p, st, cat);
+        case EPI_F32: return launch_gemm4_tc_t<EPI_F32>(h, maps, p, st, cat);
+        case EPI_RESID_LN: return launch_gemm4_tc_t<EPI_RESID_LN>(h, maps, p, st, cat);
+    }
+    return fail(TVB_ERR_INVALID, "unknown epilogue %d", epi);
+}
 // CTA-pair GEMM; maps.b must be the box-128 weight map, maps.out / maps.resid the epilogue maps of the destination.
 static int launch_gemm2_tc(tvb_handle* h, int epi, const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st, int num_sms, int cat = PC_GEMM) {
     if (p.M % 256 || p.N % 256 || p.K % GEMM_BK || p.K1 % GEMM_BK) return fail(TVB_ERR_INVALID, "gemm shape %dx%dx%d not tileable by CTA pairs", p.M, p.N, p.K);
@@ -749,6 +792,10 @@ static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, Li
             if (epi == LE_PLAIN || epi == LE_GELU) maps.out = out->tm_out;
             else maps.out = f32_map(h, out_f32);
             maps.resid = f32_map(h, p.resid);
+            if (h->opt_gemm_mc && Mp % 512 == 0) {
+                maps.b = lin.tm3;
+                return launch_gemm4_tc(h, e, maps, p, st, cat);
+            }
             return launch_gemm2_tc(h, e, maps, p, st, h->num_sms, cat);
         }
         return launch_gemm_tc(h, e, a.tm, a2 ? a2->tm : a.tm, lin.tm, p, st, h->num_sms, cat);
@@ -1033,10 +1080,11 @@ extern "C" int tvb_debug_gemm_bf16(int device, const void* a_dev, const void* w_
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(TVB_ERR_INVALID, "sm_100a device required");
-    const bool pair = (epilogue & 0x100) != 0;
+    const bool mc = (epilogue & 0x200) != 0;
+    const bool pair = (epilogue & 0x100) != 0 || mc;
     CUtensorMap tmA, tmB;
     TRY(make_tmap(&tmA, a_dev, M, K, K, 128));
-    TRY(make_tmap(&tmB, w_dev, N, K, K, pair ? 128 : GEMM_BN));
+    TRY(make_tmap(&tmB, w_dev, N, K, K, mc ? 64 : pair ? 128 : GEMM_BN));
     GemmParams p{};
     p.M = M; p.N = N; p.K = K; p.K1 = K; p.bias = bias_dev; p.resid = resid_dev; p.out_f32 = out_f32_dev;
     p.out_bf16 = static_cast<bf16*>(out_bf16_dev); p.ld_out = N;
@@ -1048,6 +1096,7 @@ extern "C" int tvb_debug_gemm_bf16(int device, const void* a_dev, const void* w_
         else TRY(make_tmap(&maps.out, out_f32_dev, M, N, N, 32, 32, true));
         if (e == EPI_RESID_F32) TRY(make_tmap(&maps.resid, resid_dev, M, N, N, 32, 32, true));
         else maps.resid = maps.out;
+        if (mc) return launch_gemm4_tc(nullptr, e, maps, p, static_cast<cudaStream_t>(stream));
         return launch_gemm2_tc(nullptr, e, maps, p, static_cast<cudaStream_t>(stream), prop.multiProcessorCount);
     }
     return launch_gemm_tc(nullptr, epilogue, tmA, tmA, tmB, p, static_cast<cudaStream_t>(stream), prop.multiProcessorCount);
