@@ -72,7 +72,7 @@ int tvb_get_precision(const tvb_handle* h);
 /* Ablation / cross-check switches of the bf16 path: "attn_tc" and "conv_tc" (1 = tcgen05 kernel, default;
  * 0 = the CUDA-core kernel of the same op; both are GPU kernels of this library, there is no CPU path),
  * "gemm_2cta" (1 = CTA-pair tcgen05 GEMM, default; 0 = single-CTA tcgen05 GEMM), "gemm_mc" (1 = two CTA pairs per cluster
- * sharing the W tile by TMA multicast, default; 0 = independent pairs), "attn_v" (4 = attn4_tc.cuh, default;
+ * sharing the W tile by TMA multicast, default; 0 = independent pairs), "attn_v" (5 = attn5_tc.cuh, 4 = attn4_tc.cuh,
  * 3 = attn_tc.cuh), "attn_poly" (attention v4: 0 = every exp2 on MUFU; 2/3/4 = one element pair in n on the FMA-pipe
  * polynomial), "ln_fuse" (1 = LayerNorm re-applied in the residual GEMM epilogue instead of materialising the fp32
  * stream, default; 0 = separate fp32 LayerNorm output), and "profile" (see tvb_profile_read). */
@@ -107,6 +107,19 @@ int tvb_solve(tvb_handle* h, int32_t solver, const int64_t* x_dev, const float* 
               const float* t_span_host, float gradient_scale, int32_t speech_prompt,
               const float* prompt_noise_dev, float* out_mel_dev, float* step_v_dev, void* stream);
 
+/* ---- decoder glue either side of the sampler; stateless, no handle ----
+ * Replaces: process_unit (util/model_util.py:50-54): repeat every unit `rep` (= sampling_rate // 50 = 441) times, cut into
+ * windows of `hop` (= 256) samples, majority vote per window (ties -> smallest value, as torch.mode).
+ * units_dev int64 [n_units] -> out_dev int64 [n_out], n_out = n_units * rep / hop. */
+int tvb_process_unit(int device, const int64_t* units_dev, int64_t n_units, int32_t rep, int32_t hop, int64_t* out_dev, int64_t n_out,
+                     void* stream);
+/* Replaces: get_mel (util/model_util.py:24-38) -> mel_spectrogram (vocoder/meldataset.py:55-78) + the (mel - mean) / std
+ * normalisation of model_util.py:82.  wav_dev fp32 [n_samples] already clamped to [-1, 1]; reflect padding (n_fft - hop) / 2,
+ * periodic Hann window of n_fft, hop `hop`, center = False; mel_basis_dev fp32 [n_mels, n_fft / 2 + 1];
+ * out_dev fp32 [n_mels, n_frames] with n_frames = (n_samples + n_fft - hop - n_fft) / hop + 1. */
+int tvb_mel_spectrogram(int device, const float* wav_dev, int64_t n_samples, int32_t n_fft, int32_t hop, int32_t n_mels,
+                        const float* mel_basis_dev, float mean, float std, float* out_dev, int64_t n_frames, void* stream);
+
 /* Per-kernel timing (bench.py's roofline leg).  With tvb_set_option(h, "profile", 1) every kernel launch is bracketed by
  * CUDA events on the launching stream; tvb_profile_read synchronises the device, sums the elapsed milliseconds and launch
  * counts by category into two arrays of 16 entries and resets the log.
@@ -132,10 +145,14 @@ int tvb_debug_gemm_bf16(int device, const void* a_dev, const void* w_dev, const 
 
 /* Kernel-level test hook (tests/ only): the tcgen05 attention kernel alone on packed [rows, 3H] bf16 q|k|v rows (q pre-scaled
  * by head_dim^-0.5 * log2(e)); sequence s occupies rows [seq_start[s], seq_start[s] + seq_len[s]).  ctx_dev bf16 [rows, H].
- * version: 4 = attn4_tc.cuh, 3 = attn_tc.cuh (P in tensor memory), 2 = attn_tc.cuh (P through shared memory).  Synchronises. */
+ * version: 5 = attn5_tc.cuh, 4 = attn4_tc.cuh, 3 = attn_tc.cuh (P in tensor memory), 2 = attn_tc.cuh (P through shared memory).  Synchronises. */
 int tvb_debug_attention(int device, const void* qkv_dev, void* ctx_dev, const int32_t* seq_start_host, const int32_t* seq_len_host,
                         int32_t nseq, int32_t rows, int32_t H, int32_t nheads, const float* slopes_dev, int32_t version,
                         int32_t poly, void* stream);
+
+/* Test hook: attention v4 launches write clock64() stamps of their first 16 CTAs into this device buffer (16 x 256 int64;
+ * layout in attn4_tc.cuh); NULL (default) disables. */
+int tvb_debug_set_trace(void* trace_dev);
 
 const char* tvb_last_error(void);
 const char* tvb_version(void);

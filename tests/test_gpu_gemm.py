@@ -61,7 +61,7 @@ def test_gemm_epilogues(epi, pair):
         want = ref; got = of
         assert (ob.float() - ref.to(torch.bfloat16).float()).abs().max().item() < 0.05
     err = (got - want).abs().max().item()
-    assert err < 0.03, f"epilogue {epi}: max abs err {err}"
+    assert err < 0.04, f"epilogue {epi}: max abs err {err}"      # one bf16 ulp at |x| in [4, 8) is 0.03125
 
 
 @pytest.mark.timeout(300)
@@ -89,4 +89,4 @@ def test_gemm_cluster4_epilogues(epi):
         want = ref; got = of
         assert (ob.float() - ref.to(torch.bfloat16).float()).abs().max().item() < 0.05
     err = (got - want).abs().max().item()
-    assert err < 0.03, f"epilogue {epi}: max abs err {err}"
+    assert err < 0.04, f"epilogue {epi}: max abs err {err}"      # one bf16 ulp at |x| in [4, 8) is 0.03125

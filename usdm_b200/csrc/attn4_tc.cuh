@@ -66,7 +66,12 @@ __device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
 template <int POLY>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn4_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ ctx, int H, int nheads,
-             const float* __restrict__ slopes, const int4* __restrict__ work) {
+             const float* __restrict__ slopes, const int4* __restrict__ work, long long* __restrict__ trace) {
+    // trace (test hook, normally nullptr): clock64() stamps of the first 16 CTAs, 256 slots each: [0] entry, [1] set-up done,
+    // half A [16+2j] scores of block j visible / [17+2j] P of block j handed over, [80] output stored; half B the same at +80;
+    // MMA thread [176] Q landed, [177+n] P of step n received.
+    long long* tr = (trace != nullptr && blockIdx.x < 16) ? trace + blockIdx.x * 256 : nullptr;
+    if (tr && threadIdx.x == 128) tr[0] = clock64();
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A4_SMEM_BAR);
     uint64_t* q_full = bars + 0;
@@ -128,6 +133,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tr && threadIdx.x == 128) tr[1] = clock64();
 
     if (warp_idx < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -179,6 +185,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                 const int slot = j % A4_KV_STAGES;
                 mbar_wait(&p_ready[n % 3], (n / 3) & 1);
                 tc_fence_after();
+                if (tr && n < 70) tr[177 + n] = clock64();
                 const uint32_t sV = smem_u32(smem + A4_SMEM_KV + slot * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES);
                 const uint32_t tP = tmem_base + (n % 3) * 128;
                 const uint32_t tO = tmem_base + 384 + half * 64;
@@ -192,6 +199,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
             };
             mbar_wait(q_full, 0);
             tc_fence_after();
+            if (tr) tr[176] = clock64();
             for (int n = 0; n < 3 && n < total; ++n) issue_qk(n);
             for (int n = 0; n < total; ++n) {
                 issue_pv(n);
@@ -224,6 +232,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                 const float c_row = diag ? 0.f : -slope2 * fabsf(static_cast<float>(i - k0));
                 mbar_wait(&s_full[buf], (n / 3) & 1);
                 tc_fence_after();
+                if (tr && r == 0 && j < 32) tr[16 + half * 80 + 2 * j] = clock64();
                 // s[0,64): bf16 pairs of P (output); fast path: s[64,96) / s[96,128) double-buffer 32-column chunks of S
                 uint32_t s[128];
                 uint32_t(&ca)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
@@ -375,6 +384,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&p_ready[buf]);
+                if (tr && r == 0 && j < 32) tr[17 + half * 80 + 2 * j] = clock64();
             }
             // epilogue: O / l -> ctx (bf16), only rows that belong to the sequence
             mbar_wait(&pv_done[half], (nkb - 1) & 1);
@@ -400,6 +410,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                     reinterpret_cast<uint4*>(dst + c * 16)[1] = b;
                 }
             }
+            if (tr && r == 0) tr[80 + half * 80] = clock64();
         }
     }
     tc_fence_before();
@@ -408,6 +419,11 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
+}
+
+inline long long*& attn_trace_ptr() {      // test hook (tvb_debug_set_trace): device buffer of 16 x 256 int64, or nullptr
+    static long long* p = nullptr;
+    return p;
 }
 
 template <int POLY>
@@ -419,7 +435,7 @@ inline cudaError_t launch_attn4_t(const CUtensorMap& tmQKV, __nv_bfloat16* ctx, 
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    attn4_kernel<POLY><<<nwork * nheads, ATT_THREADS, A4_SMEM_BYTES, st>>>(tmQKV, ctx, H, nheads, slopes, work);
+    attn4_kernel<POLY><<<nwork * nheads, ATT_THREADS, A4_SMEM_BYTES, st>>>(tmQKV, ctx, H, nheads, slopes, work, attn_trace_ptr());
     return cudaGetLastError();
 }
 // The q columns of tmQKV must have been produced with W_q, b_q scaled by head_dim^-0.5 * log2(e).

@@ -16,8 +16,10 @@
 #include "../../include/tvb.h"
 #include "attn_tc.cuh"
 #include "attn4_tc.cuh"
+#include "attn5_tc.cuh"
 #include "conv_tc.cuh"
 #include "gemm_tc.cuh"
+#include "glue.cuh"
 #include "simt.cuh"
 
 using namespace tvb;
@@ -512,7 +514,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     else if (!strcmp(name, "gemm_2cta")) h->opt_gemm_2cta = value ? 1 : 0;
     else if (!strcmp(name, "gemm_mc")) h->opt_gemm_mc = value ? 1 : 0;
     else if (!strcmp(name, "attn_ptmem")) h->opt_attn_ptmem = value ? 1 : 0;
-    else if (!strcmp(name, "attn_v")) { if (value != 3 && value != 4) return fail(TVB_ERR_INVALID, "attn_v must be 3 or 4"); h->opt_attn_v = value; }
+    else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 5) return fail(TVB_ERR_INVALID, "attn_v must be 3, 4 or 5"); h->opt_attn_v = value; }
     else if (!strcmp(name, "attn_poly")) { if (value != 0 && value != 2 && value != 3 && value != 4) return fail(TVB_ERR_INVALID, "attn_poly must be 0, 2, 3 or 4"); h->opt_attn_poly = value; }
     else if (!strcmp(name, "ln_fuse")) h->opt_ln_fuse = value ? 1 : 0;
     else if (!strcmp(name, "profile")) { h->profile = value ? 1 : 0; h->ev_used = 0; h->ev_cat.clear(); }
@@ -832,7 +834,9 @@ static int attention(tvb_handle* h, cudaStream_t st) {
     const int H = h->cfg.hidden_size, nh = h->cfg.num_attention_heads;
     ProfScope ps(h, st, PC_ATTN);
     // bf16 path: q carries head_dim^-0.5 * log2(e) (tvb_finalize_weights), so tensor-core scores are already in the log2 domain
-    if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 4) {
+    if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 5) {
+        CK(launch_attn5_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_poly, st));
+    } else if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 4) {
         CK(launch_attn4_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_poly, st));
     } else if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc) {
         CK(launch_attn_tc_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_ptmem != 0, 1.0f, st));
@@ -1126,7 +1130,8 @@ extern "C" int tvb_debug_attention(int device, const void* qkv_dev, void* ctx_de
     int rc = make_tmap(&tm, qkv_dev, rows, 3 * H, 3 * H, 128);
     if (rc == TVB_OK) {
         cudaError_t e;
-        if (version == 4) e = launch_attn4_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, st);
+        if (version == 5) e = launch_attn5_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, st);
+        else if (version == 4) e = launch_attn4_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, st);
         else e = launch_attn_tc_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), version != 2, 1.0f, st);
         if (e != cudaSuccess) rc = fail(TVB_ERR_CUDA, "attention launch: %s", cudaGetErrorString(e));
     }
@@ -1134,4 +1139,47 @@ extern "C" int tvb_debug_attention(int device, const void* qkv_dev, void* ctx_de
     cudaFree(d_work);
     if (rc == TVB_OK && e2 != cudaSuccess) return fail(TVB_ERR_CUDA, "attention kernel: %s", cudaGetErrorString(e2));
     return rc;
+}
+
+// Test hook: device buffer (16 x 256 int64) that attention v4 launches fill with clock64() stamps of their first 16 CTAs; nullptr disables.
+extern "C" int tvb_debug_set_trace(void* trace_dev) {
+    attn_trace_ptr() = static_cast<long long*>(trace_dev);
+    return TVB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// decoder glue: stateless device functions either side of the sampler
+// ----------------------------------------------------------------------------------------------------------------
+extern "C" int tvb_process_unit(int device, const int64_t* units_dev, int64_t n_units, int32_t rep, int32_t hop, int64_t* out_dev,
+                                int64_t n_out, void* stream) {
+    if (!units_dev || !out_dev) return fail(TVB_ERR_INVALID, "null argument");
+    if (rep <= 0 || hop <= 0 || n_units < 0) return fail(TVB_ERR_INVALID, "bad rep / hop / n_units");
+    if (n_out != n_units * rep / hop) return fail(TVB_ERR_INVALID, "n_out must be n_units * rep / hop = %lld", (long long)(n_units * rep / hop));
+    if (n_out == 0) return TVB_OK;
+    CK(cudaSetDevice(device));
+    k_process_unit<<<static_cast<unsigned>((n_out + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(units_dev, n_units, rep, hop, out_dev, n_out);
+    CKL();
+    return TVB_OK;
+}
+
+extern "C" int tvb_mel_spectrogram(int device, const float* wav_dev, int64_t n_samples, int32_t n_fft, int32_t hop, int32_t n_mels,
+                                   const float* mel_basis_dev, float mean, float std, float* out_dev, int64_t n_frames, void* stream) {
+    if (!wav_dev || !mel_basis_dev || !out_dev) return fail(TVB_ERR_INVALID, "null argument");
+    if (hop <= 0 || hop > n_fft || (n_fft - hop) % 2 != 0 || n_mels <= 0 || std == 0.f) return fail(TVB_ERR_INVALID, "bad STFT / mel parameters");
+    const int pad = (n_fft - hop) / 2;
+    if (n_samples <= pad) return fail(TVB_ERR_INVALID, "signal of %lld samples is too short for reflect padding %d", (long long)n_samples, pad);
+    const int64_t want = (n_samples + 2 * pad - n_fft) / hop + 1;
+    if (n_frames != want) return fail(TVB_ERR_INVALID, "n_frames must be %lld", (long long)want);
+    CK(cudaSetDevice(device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = static_cast<unsigned>(n_frames);
+    switch (n_fft) {
+        case 256: k_mel_spectrogram<256><<<grid, 512, 0, st>>>(wav_dev, n_samples, hop, n_mels, mel_basis_dev, mean, 1.0f / std, out_dev, n_frames); break;
+        case 512: k_mel_spectrogram<512><<<grid, 512, 0, st>>>(wav_dev, n_samples, hop, n_mels, mel_basis_dev, mean, 1.0f / std, out_dev, n_frames); break;
+        case 1024: k_mel_spectrogram<1024><<<grid, 512, 0, st>>>(wav_dev, n_samples, hop, n_mels, mel_basis_dev, mean, 1.0f / std, out_dev, n_frames); break;
+        case 2048: k_mel_spectrogram<2048><<<grid, 512, 0, st>>>(wav_dev, n_samples, hop, n_mels, mel_basis_dev, mean, 1.0f / std, out_dev, n_frames); break;
+        default: return fail(TVB_ERR_INVALID, "unsupported n_fft %d (256, 512, 1024, 2048)", n_fft);
+    }
+    CKL();
+    return TVB_OK;
 }

@@ -39,12 +39,15 @@ _SIGNATURES = {
     "tvb_sample_cfg": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, _P, _P]),
     "tvb_solve": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                             C.POINTER(C.c_float), C.c_float, C.c_int32, _P, _P, _P, _P]),
+    "tvb_process_unit": (C.c_int, [C.c_int, _P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
+    "tvb_mel_spectrogram": (C.c_int, [C.c_int, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, C.c_float, C.c_float, _P, C.c_int64, _P]),
     "tvb_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "tvb_kernel_launches": (C.c_int64, [_P]),
     "tvb_device_bytes": (C.c_int64, [_P]),
     "tvb_debug_gemm_bf16": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "tvb_debug_attention": (C.c_int, [C.c_int, _P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, _P, C.c_int32, C.c_int32, _P]),
+    "tvb_debug_set_trace": (C.c_int, [_P]),
     "tvb_last_error": (C.c_char_p, []),
     "tvb_version": (C.c_char_p, []),
 }
