@@ -407,6 +407,10 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                     mbar_arrive(&p_ready[buf]);
 
             }
+            // An item whose second half has no rows is skipped by the half-B threads.  They must not run ahead to the s_full wait
+            // of their next step while this item's QK MMAs are still outstanding (parity waits are only unambiguous within one
+            // phase): they wait on a named barrier that the half-A threads reach after observing the item's last scores.
+            if (!w.two) asm volatile("bar.arrive 1, 256;" ::: "memory");
             // epilogue: read O, hand the accumulator back, then O / l -> ctx (bf16), only rows that belong to the sequence
             mbar_wait(&pv_done[half], (pvbase + nkb - 1) & 1);
             tc_fence_after();
@@ -428,6 +432,8 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                                    pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv));
             }
             pvbase += nkb;
+            } else {
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             gbase += nkb * w.nh;
         }

@@ -237,8 +237,9 @@ constexpr int G2_B_BYTES = 128 * GEMM_BK * 2;                // 16 KB (this CTA'
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 constexpr int G2_EPI_WARPS = 8;
 constexpr int G2_EPI_TILE = 4096;                            // 32 rows x 128 B
+constexpr int G2_EPI_BUFS = 3;                               // staging tiles per epilogue warp: computing / residual in flight / storing
 constexpr int G2_SMEM_EPI = G2_STAGES * G2_STAGE_BYTES;
-constexpr int G2_SMEM_BAR = G2_SMEM_EPI + G2_EPI_WARPS * 2 * G2_EPI_TILE;
+constexpr int G2_SMEM_BAR = G2_SMEM_EPI + G2_EPI_WARPS * G2_EPI_BUFS * G2_EPI_TILE;
 constexpr int G2_SMEM_BYTES = G2_SMEM_BAR + 1024 + 512;
 constexpr int G2_THREADS = 320;
 
@@ -263,8 +264,8 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
     uint64_t* empty_bar = full_bar + G2_STAGES;
     uint64_t* tfull_bar = empty_bar + G2_STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint64_t* rbar = tempty_bar + 2;                  // [8 warps][2 buffers] residual-tile arrival
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 2 * G2_EPI_WARPS);
+    uint64_t* rbar = tempty_bar + 2;                  // [8 warps][G2_EPI_BUFS] residual-tile arrival
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + G2_EPI_BUFS * G2_EPI_WARPS);
 
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = cluster_ctarank();
@@ -283,7 +284,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
     if (warp_idx == 1 && lane == 0) {
         for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NP); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * G2_EPI_WARPS); }
-        for (int s = 0; s < 2 * G2_EPI_WARPS; ++s) mbar_init(&rbar[s], 1);
+        for (int s = 0; s < G2_EPI_BUFS * G2_EPI_WARPS; ++s) mbar_init(&rbar[s], 1);
         fence_barrier_init();
     }
     if (warp_idx == 2) tmem_alloc_2cta<512>(tmem_slot);
@@ -347,10 +348,12 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
         const int ew = warp_idx - 2;
         const int quad = warp_idx & 3;
         const int chalf = ew >> 2;                                // which 128 of the 256 accumulator columns
-        uint8_t* stg = smem + G2_SMEM_EPI + ew * 2 * G2_EPI_TILE;
-        uint64_t* rb = rbar + ew * 2;
+        uint8_t* stg = smem + G2_SMEM_EPI + ew * G2_EPI_BUFS * G2_EPI_TILE;
+        uint64_t* rb = rbar + ew * G2_EPI_BUFS;
         const int r7 = lane & 7;
-        uint32_t kc = 0;                                          // running chunk counter -> staging buffer / parity
+        uint32_t kc = 0;                                          // running chunk counter
+        int buf = 0;                                              // kc % G2_EPI_BUFS
+        uint32_t bpar = 0;                                        // (kc / G2_EPI_BUFS) & 1: parity of this buffer's residual barrier
         auto chunk_coords = [&](int tile, int c, int& col, int& row) {
             row = tile_m0(tile) + static_cast<int>(cta) * 128 + quad * 32;
             col = (tile % tiles_n) * 256 + chalf * 128 + c * kChunkCols;
@@ -371,24 +374,25 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
             const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256 + chalf * 128;
 #pragma unroll 1
             for (int c = 0; c < kChunks; ++c, ++kc) {
-                const int buf = kc & 1;
                 uint8_t* tile_s = stg + buf * G2_EPI_TILE;
+                const int nbuf = (buf + 1 == G2_EPI_BUFS) ? 0 : buf + 1;
                 int col, row;
                 chunk_coords(tile, c, col, row);
                 if (lane == 0) {
                     if constexpr (kResid) {
-                        // the other buffer's last store must have finished reading before the next residual lands in it
-                        tma_store_wait_read<0>();
+                        // buffer nbuf was last used by the chunk two back: its store must have finished reading before the next
+                        // residual tile lands there (the store of the previous chunk may still be in flight)
+                        tma_store_wait_read<1>();
                         int nt = tile, nc = c + 1;
                         if (nc == kChunks) { nc = 0; nt = tile + num_clusters; }
                         if (nt < num_tiles) {
                             int ncol, nrow;
                             chunk_coords(nt, nc, ncol, nrow);
-                            mbar_arrive_expect_tx(&rb[buf ^ 1], G2_EPI_TILE);
-                            tma_load_2d(stg + (buf ^ 1) * G2_EPI_TILE, &tm.resid, &rb[buf ^ 1], ncol, nrow);
+                            mbar_arrive_expect_tx(&rb[nbuf], G2_EPI_TILE);
+                            tma_load_2d(stg + nbuf * G2_EPI_TILE, &tm.resid, &rb[nbuf], ncol, nrow);
                         }
                     } else {
-                        tma_store_wait_read<1>();                 // the store issued two chunks ago (same buffer) is done reading
+                        tma_store_wait_read<G2_EPI_BUFS - 1>();   // the store issued G2_EPI_BUFS chunks ago (same buffer) is done reading
                     }
                 }
                 __syncwarp();
@@ -415,7 +419,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                 }
                 uint8_t* rowp = tile_s + lane * 128;               // this thread's row of the staging tile
                 if constexpr (EPI == EPI_RESID_F32) {
-                    mbar_wait(&rb[buf], (kc >> 1) & 1);            // residual tile landed (async proxy -> visible after wait)
+                    mbar_wait(&rb[buf], bpar);                     // residual tile landed (async proxy -> visible after wait)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4* q4 = reinterpret_cast<float4*>(rowp + ((j ^ r7) << 4));
@@ -426,7 +430,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                     const float2 st = p.ln_stats[row + lane];      // (mean, rstd) of this thread's residual row
                     const float4* g4 = reinterpret_cast<const float4*>(p.ln_g + col);
                     const float4* b4 = reinterpret_cast<const float4*>(p.ln_b + col);
-                    mbar_wait(&rb[buf], (kc >> 1) & 1);
+                    mbar_wait(&rb[buf], bpar);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4* q4 = reinterpret_cast<float4*>(rowp + ((j ^ r7) << 4));
@@ -458,6 +462,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                     tma_store_2d(&tm.out, tile_s, col, row);
                     tma_store_commit();
                 }
+                if (++buf == G2_EPI_BUFS) { buf = 0; bpar ^= 1; }
             }
             tc_fence_before();
             __syncwarp();
