@@ -65,7 +65,7 @@ def _run(lens, version, poly, seed=0, scale=1.0):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("version,poly", [(6, 0), (6, 2), (6, 3), (6, 4), (5, 0), (5, 2), (5, 3), (5, 4), (4, 0), (4, 2), (4, 3), (4, 4), (3, 0), (2, 0)])
+@pytest.mark.parametrize("version,poly", [(7, 0), (7, 2), (7, 3), (7, 4), (6, 0), (6, 2), (6, 3), (6, 4), (5, 0), (5, 2), (5, 3), (5, 4), (4, 0), (4, 2), (4, 3), (4, 4), (3, 0), (2, 0)])
 def test_attention_kernel_vs_fp32_math(version, poly):
     # lengths cover: 1 key, < 1 block, exact block multiples, odd tails, one / two query halves, the configs[1] length
     lens = [1134, 1, 127, 128, 129, 256, 257, 384, 700, 389, 2, 513]
@@ -75,7 +75,7 @@ def test_attention_kernel_vs_fp32_math(version, poly):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("version,poly", [(4, 0), (4, 3), (5, 0), (5, 3), (6, 0), (6, 3)])
+@pytest.mark.parametrize("version,poly", [(4, 0), (4, 3), (5, 0), (5, 3), (6, 0), (6, 3), (7, 0), (7, 3)])
 def test_attention_peaky_scores_exercise_rescale(version, poly):
     """Large-magnitude q.k (std ~ 40 in the log2 domain) so that block maxima jump by more than 2^16 and the lazy O rescale runs."""
     rel, mx = _run([1134, 640, 300], version, poly, seed=1, scale=3.0)
@@ -84,7 +84,7 @@ def test_attention_peaky_scores_exercise_rescale(version, poly):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("version", [4, 5, 6])
+@pytest.mark.parametrize("version", [4, 5, 6, 7])
 def test_attention_long_form(version):
     """configs[2]-like length (30 s + prompt): 23 key blocks, 12 query tiles per head."""
     rel, mx = _run([2856, 2584], version, 0, seed=2)

@@ -82,29 +82,26 @@ def bench_attn(out):
     def run(version, poly):
         engine.check(lib.tvb_debug_attention(0, P(qkv), P(ctx), s_arr, l_arr, len(lens), rows, H, NH, P(slopes), version, poly, ST()))
 
-    for version, poly in [(3, 0), (4, 0), (4, 3), (5, 0), (5, 3)]:
-        for _ in range(3):
-            run(version, poly)
-        t = timed(lambda: run(version, poly), 20)       # includes the hook's per-call stream sync + work-list upload: ~tens of us
-        out.append(dict(kind="attn", version=version, poly=poly, us=t * 1e6, tflops=flops / t / 1e12))
-        print(out[-1], flush=True)
-    # trace of v4
-    trace = torch.zeros(16 * 256, dtype=torch.int64, device="cuda")
-    engine.check(lib.tvb_debug_set_trace(P(trace)))
-    run(4, 0)
-    torch.cuda.synchronize()
-    engine.check(lib.tvb_debug_set_trace(None))
-    tr = trace.cpu().view(16, 256)
-    for cta in (0, 1, 5, 15):
-        row = tr[cta].tolist()
-        t0 = row[0]
-        rel = lambda v: (v - t0) if v else None
-        d = dict(kind="attn_trace", cta=cta, setup=rel(row[1]), q_landed=rel(row[176]),
-                 A_s_ready=[rel(row[16 + 2 * j]) for j in range(9)], A_p_done=[rel(row[17 + 2 * j]) for j in range(9)], A_end=rel(row[80]),
-                 B_s_ready=[rel(row[96 + 2 * j]) for j in range(9)], B_p_done=[rel(row[97 + 2 * j]) for j in range(9)], B_end=rel(row[160]),
-                 mma_p_recv=[rel(row[177 + n]) for n in range(18)])
-        out.append(d)
-        print(d, flush=True)
+    for tv in (4, 7):
+      # trace of v4 / v7 (the hook's own per-call overhead makes wall-clock timing of single launches meaningless here)
+      for _ in range(3):
+          run(tv, 0)
+      trace = torch.zeros(16 * 256, dtype=torch.int64, device="cuda")
+      engine.check(lib.tvb_debug_set_trace(P(trace)))
+      run(tv, 0)
+      torch.cuda.synchronize()
+      engine.check(lib.tvb_debug_set_trace(None))
+      tr = trace.cpu().view(16, 256)
+      for cta in (0, 5):
+          row = tr[cta].tolist()
+          t0 = row[0]
+          rel = lambda v: (v - t0) if v else None
+          d = dict(kind="attn_trace", version=tv, cta=cta, setup=rel(row[1]), q_landed=rel(row[176]),
+                   A_s_ready=[rel(row[16 + 2 * j]) for j in range(9)], A_p_done=[rel(row[17 + 2 * j]) for j in range(9)], A_end=rel(row[80]),
+                   B_s_ready=[rel(row[96 + 2 * j]) for j in range(9)], B_p_done=[rel(row[97 + 2 * j]) for j in range(9)], B_end=rel(row[160]),
+                   mma_p_recv=[rel(row[177 + n]) for n in range(18)])
+          out.append(d)
+          print(d, flush=True)
 
 
 if __name__ == "__main__":

@@ -18,6 +18,7 @@
 #include "attn4_tc.cuh"
 #include "attn5_tc.cuh"
 #include "attn6_tc.cuh"
+#include "attn7_tc.cuh"
 #include "conv_tc.cuh"
 #include "gemm_tc.cuh"
 #include "glue.cuh"
@@ -516,7 +517,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     else if (!strcmp(name, "gemm_2cta")) h->opt_gemm_2cta = value ? 1 : 0;
     else if (!strcmp(name, "gemm_mc")) h->opt_gemm_mc = value ? 1 : 0;
     else if (!strcmp(name, "attn_ptmem")) h->opt_attn_ptmem = value ? 1 : 0;
-    else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 6) return fail(TVB_ERR_INVALID, "attn_v must be 3, 4, 5 or 6"); h->opt_attn_v = value; }
+    else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 7) return fail(TVB_ERR_INVALID, "attn_v must be 3 .. 7"); h->opt_attn_v = value; }
     else if (!strcmp(name, "attn_poly")) { if (value != 0 && value != 2 && value != 3 && value != 4) return fail(TVB_ERR_INVALID, "attn_poly must be 0, 2, 3 or 4"); h->opt_attn_poly = value; }
     else if (!strcmp(name, "ln_fuse")) h->opt_ln_fuse = value ? 1 : 0;
     else if (!strcmp(name, "profile")) { h->profile = value ? 1 : 0; h->ev_used = 0; h->ev_cat.clear(); }
@@ -836,7 +837,9 @@ static int attention(tvb_handle* h, cudaStream_t st) {
     const int H = h->cfg.hidden_size, nh = h->cfg.num_attention_heads;
     ProfScope ps(h, st, PC_ATTN);
     // bf16 path: q carries head_dim^-0.5 * log2(e) (tvb_finalize_weights), so tensor-core scores are already in the log2 domain
-    if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 6) {
+    if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 7) {
+        CK(launch_attn7_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_poly, st));
+    } else if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 6) {
         CK(launch_attn6_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_poly, h->num_sms, st));
     } else if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 5) {
         CK(launch_attn5_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_poly, st));
@@ -1134,7 +1137,8 @@ extern "C" int tvb_debug_attention(int device, const void* qkv_dev, void* ctx_de
     int rc = make_tmap(&tm, qkv_dev, rows, 3 * H, 3 * H, 128);
     if (rc == TVB_OK) {
         cudaError_t e;
-        if (version == 6) e = launch_attn6_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, prop.multiProcessorCount, st);
+        if (version == 7) e = launch_attn7_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, st);
+        else if (version == 6) e = launch_attn6_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, prop.multiProcessorCount, st);
         else if (version == 5) e = launch_attn5_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, st);
         else if (version == 4) e = launch_attn4_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, st);
         else e = launch_attn_tc_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), version != 2, 1.0f, st);
