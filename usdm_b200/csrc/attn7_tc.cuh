@@ -93,7 +93,7 @@ attn7_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp_idx == 0) {
         // ------------------------------------------ TMA producer ------------------------------------------
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_arrive_expect_tx(q_full, nh * ATT_TILE_BYTES);
             tma_load_2d(smem + A4_SMEM_Q, &tmQKV, q_full, head * ATT_D, start + q0);
             if (two) tma_load_2d(smem + A4_SMEM_Q + ATT_TILE_BYTES, &tmQKV, q_full, head * ATT_D, start + q0 + 128);
@@ -233,7 +233,9 @@ attn7_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                             else mxa = fmaxf(mxa, fmaxf(x0, x1));
                             const uint64_t x2 = fadd2(pack2f(x0, x1), off2);
                             uint64_t p2;
-                            if (POLY > 0 && (u % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) {
+                            if (POLY >= 100 && (POLY & 1)) {
+                                p2 = x2;                                                 // timing ablation: no exponential at all
+                            } else if (POLY > 0 && POLY < 100 && (u % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) {
                                 p2 = exp2_poly2(x2);
                             } else {
                                 float lo, hi;
@@ -246,6 +248,12 @@ attn7_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                             s[c * 16 + u] = pack_bf16x2(lo, hi);
                         }
                     };
+                    if (POLY >= 100 && (POLY & 2)) {                                  // timing ablation: scores never leave TMEM
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) { ca[e] = __float_as_uint(-1.0f - e); cb[e] = __float_as_uint(-2.0f - e); }
+                        asm volatile("" : "+r"(ca[0]), "+r"(cb[0]));
+                        proc(ca, 0); proc(cb, 1); proc(ca, 2); proc(cb, 3);
+                    } else {
                     tmem_ld_32x32(tmem_S, ca);
                     tmem_ld_wait_dep(ca);
                     tmem_ld_32x32(tmem_S + 32, cb);
@@ -258,6 +266,7 @@ attn7_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                     proc(ca, 2);
                     tmem_ld_wait_dep(cb);
                     proc(cb, 3);
+                    }
                     float a0, a1;
                     unpack2f(acc2, a0, a1);
                     lsum = a0 + a1;
@@ -339,9 +348,11 @@ attn7_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                 if (j > 0 && !pv_seen) mbar_wait(&pv_done[half], (j - 1) & 1);
                 l_run += lsum;
                 // ---- bf16 pairs of P into the first 64 columns of this S buffer (A operand of the PV MMA)
+                if (!(POLY >= 100 && (POLY & 4))) {                                   // (timing ablation 104: P never stored)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) tmem_st_32x16(tmem_S + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&s[c * 16]));
                 tmem_st_wait();
+                } else { asm volatile("" :: "r"(s[0]), "r"(s[17]), "r"(s[34]), "r"(s[63])); }
                 tc_fence_before();
                 mbar_arrive(&p_ready[buf]);
                 if (tr && r == 0 && j < 32) tr[17 + half * 80 + 2 * j] = clock64();
@@ -402,6 +413,11 @@ inline cudaError_t launch_attn7_raw(const CUtensorMap& tmQKV, __nv_bfloat16* ctx
         case 2: return launch_attn7_t<2>(tmQKV, ctx, H, nheads, slopes, work, nwork, st);
         case 3: return launch_attn7_t<3>(tmQKV, ctx, H, nheads, slopes, work, nwork, st);
         case 4: return launch_attn7_t<4>(tmQKV, ctx, H, nheads, slopes, work, nwork, st);
+        // timing ablations (results are WRONG; tools/ only): 101 no exp2, 102 no TMEM score loads, 104 no P store, 107 all three
+        case 101: return launch_attn7_t<101>(tmQKV, ctx, H, nheads, slopes, work, nwork, st);
+        case 102: return launch_attn7_t<102>(tmQKV, ctx, H, nheads, slopes, work, nwork, st);
+        case 104: return launch_attn7_t<104>(tmQKV, ctx, H, nheads, slopes, work, nwork, st);
+        case 107: return launch_attn7_t<107>(tmQKV, ctx, H, nheads, slopes, work, nwork, st);
         default: return cudaErrorInvalidValue;
     }
 }

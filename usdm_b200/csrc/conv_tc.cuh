@@ -50,7 +50,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp_idx == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int g = tile % groups, m0 = (tile / groups) * CV_BM;
@@ -65,7 +65,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             }
         }
     } else if (warp_idx == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_bf16(128, 64);
             int stage = 0; uint32_t phase = 0; int it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {

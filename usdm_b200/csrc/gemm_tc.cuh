@@ -88,7 +88,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp_idx == 0) {
         // ------------------------------ TMA producer ------------------------------
-        if (lane == 0) {
+        if (elect_one()) {      // one elected lane: the compiler then keeps descriptors / addresses in uniform registers
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -109,7 +109,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp_idx == 1) {
         // ------------------------------ MMA issuer ------------------------------
-        if (lane == 0) {
+        if (elect_one()) {      // one elected lane: the compiler then keeps descriptors / addresses in uniform registers
             constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, GEMM_BN);
             int stage = 0;
             uint32_t phase = 0;
@@ -294,7 +294,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp_idx == 0) {
-        if (lane == 0) {
+        if (elect_one()) {      // one elected lane: the compiler then keeps descriptors / addresses in uniform registers
             int stage = 0; uint32_t phase = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 const int m0 = tile_m0(tile) + static_cast<int>(cta) * 128;
@@ -317,7 +317,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
             }
         }
     } else if (warp_idx == 1) {
-        if (cta == 0 && lane == 0) {
+        if (cta == 0 && elect_one()) {
             constexpr uint32_t idesc = make_idesc_bf16(256, 256);
             int stage = 0; uint32_t phase = 0; int it = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {

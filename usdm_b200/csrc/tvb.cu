@@ -131,8 +131,8 @@ struct tvb_handle {
     int opt_gemm_mc = 0;        // CTA-pair GEMM: 1 = clusters of two pairs sharing the W tile by TMA multicast, 0 = independent pairs (default:
                                 // measured 7 % slower with multicast, profiles/r01: the pair kernel is not L2->SM bound after all)
     int opt_attn_ptmem = 1;     // tcgen05 attention v3: 1 = P kept in tensor memory (TS MMA), 0 = P staged through shared memory
-    int opt_attn_v = 4;         // tcgen05 attention kernel generation: 4 = attn4_tc.cuh (default), 3 = attn_tc.cuh
-    int opt_attn_poly = 0;      // attention v4: 0 = every exp2 on MUFU, n = one element pair in n on the FMA-pipe polynomial
+    int opt_attn_v = 7;         // tcgen05 attention kernel generation: 7 = attn7_tc.cuh (default), 6 / 5 / 4 = attnN_tc.cuh, 3 = attn_tc.cuh
+    int opt_attn_poly = 3;      // attention v4+: 0 = every exp2 on MUFU, n = one element pair in n on the FMA-pipe polynomial (default 3)
     int opt_ln_fuse = 1;        // bf16 path: 1 = LayerNorm writes bf16 + (mean, rstd) only and the residual GEMM epilogue re-normalises
                                 //            the fp32 stream on the fly (EPI_RESID_LN); 0 = LayerNorm materialises the fp32 result
     int profile = 0;            // 1: bracket every kernel with CUDA events on the launching stream (bench.py roofline leg)
@@ -518,7 +518,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     else if (!strcmp(name, "gemm_mc")) h->opt_gemm_mc = value ? 1 : 0;
     else if (!strcmp(name, "attn_ptmem")) h->opt_attn_ptmem = value ? 1 : 0;
     else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 7) return fail(TVB_ERR_INVALID, "attn_v must be 3 .. 7"); h->opt_attn_v = value; }
-    else if (!strcmp(name, "attn_poly")) { if (value != 0 && value != 2 && value != 3 && value != 4) return fail(TVB_ERR_INVALID, "attn_poly must be 0, 2, 3 or 4"); h->opt_attn_poly = value; }
+    else if (!strcmp(name, "attn_poly")) { if (value != 0 && value != 2 && value != 3 && value != 4 && !(value >= 100 && value < 108)) return fail(TVB_ERR_INVALID, "attn_poly must be 0, 2, 3 or 4"); h->opt_attn_poly = value; }
     else if (!strcmp(name, "ln_fuse")) h->opt_ln_fuse = value ? 1 : 0;
     else if (!strcmp(name, "profile")) { h->profile = value ? 1 : 0; h->ev_used = 0; h->ev_cat.clear(); }
     else return fail(TVB_ERR_INVALID, "unknown option %s", name);
