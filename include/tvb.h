@@ -72,7 +72,7 @@ int tvb_get_precision(const tvb_handle* h);
 /* Ablation / cross-check switches of the bf16 path: "attn_tc" and "conv_tc" (1 = tcgen05 kernel, default;
  * 0 = the CUDA-core kernel of the same op; both are GPU kernels of this library, there is no CPU path),
  * "gemm_2cta" (1 = CTA-pair tcgen05 GEMM, default; 0 = single-CTA tcgen05 GEMM), "gemm_mc" (1 = two CTA pairs per cluster
- * sharing the W tile by TMA multicast; 0 = independent pairs, default), "attn_v" (7 = attn7_tc.cuh, 6 = attn6_tc.cuh, 5 = attn5_tc.cuh, 4 = attn4_tc.cuh,
+ * sharing the W tile by TMA multicast; 0 = independent pairs, default), "attn_v" (8 = attn8_tc.cuh, 7 = attn7_tc.cuh, 6 = attn6_tc.cuh, 5 = attn5_tc.cuh, 4 = attn4_tc.cuh,
  * 3 = attn_tc.cuh), "attn_poly" (attention v4: 0 = every exp2 on MUFU; 2/3/4 = one element pair in n on the FMA-pipe
  * polynomial), "ln_fuse" (1 = LayerNorm re-applied in the residual GEMM epilogue instead of materialising the fp32
  * stream, default; 0 = separate fp32 LayerNorm output), and "profile" (see tvb_profile_read). */
@@ -145,7 +145,7 @@ int tvb_debug_gemm_bf16(int device, const void* a_dev, const void* w_dev, const 
 
 /* Kernel-level test hook (tests/ only): the tcgen05 attention kernel alone on packed [rows, 3H] bf16 q|k|v rows (q pre-scaled
  * by head_dim^-0.5 * log2(e)); sequence s occupies rows [seq_start[s], seq_start[s] + seq_len[s]).  ctx_dev bf16 [rows, H].
- * version: 7 = attn7_tc.cuh (two issue warps), 6 = attn6_tc.cuh (persistent), 5 = attn5_tc.cuh, 4 = attn4_tc.cuh, 3 = attn_tc.cuh (P in tensor memory), 2 = attn_tc.cuh (P through shared memory).  Synchronises. */
+ * version: 8 = attn8_tc.cuh (persistent + two issue warps), 7 = attn7_tc.cuh (two issue warps), 6 = attn6_tc.cuh (persistent), 5 = attn5_tc.cuh, 4 = attn4_tc.cuh, 3 = attn_tc.cuh (P in tensor memory), 2 = attn_tc.cuh (P through shared memory).  Synchronises. */
 int tvb_debug_attention(int device, const void* qkv_dev, void* ctx_dev, const int32_t* seq_start_host, const int32_t* seq_len_host,
                         int32_t nseq, int32_t rows, int32_t H, int32_t nheads, const float* slopes_dev, int32_t version,
                         int32_t poly, void* stream);

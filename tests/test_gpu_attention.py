@@ -65,7 +65,7 @@ def _run(lens, version, poly, seed=0, scale=1.0):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("version,poly", [(7, 0), (7, 2), (7, 3), (7, 4), (6, 0), (6, 2), (6, 3), (6, 4), (5, 0), (5, 2), (5, 3), (5, 4), (4, 0), (4, 2), (4, 3), (4, 4), (3, 0), (2, 0)])
+@pytest.mark.parametrize("version,poly", [(8, 0), (8, 2), (8, 3), (8, 4), (7, 0), (7, 2), (7, 3), (7, 4), (6, 0), (6, 2), (6, 3), (6, 4), (5, 0), (5, 2), (5, 3), (5, 4), (4, 0), (4, 2), (4, 3), (4, 4), (3, 0), (2, 0)])
 def test_attention_kernel_vs_fp32_math(version, poly):
     # lengths cover: 1 key, < 1 block, exact block multiples, odd tails, one / two query halves, the configs[1] length
     lens = [1134, 1, 127, 128, 129, 256, 257, 384, 700, 389, 2, 513]
@@ -75,7 +75,7 @@ def test_attention_kernel_vs_fp32_math(version, poly):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("version,poly", [(4, 0), (4, 3), (5, 0), (5, 3), (6, 0), (6, 3), (7, 0), (7, 3)])
+@pytest.mark.parametrize("version,poly", [(4, 0), (4, 3), (5, 0), (5, 3), (6, 0), (6, 3), (7, 0), (7, 3), (8, 0), (8, 3)])
 def test_attention_peaky_scores_exercise_rescale(version, poly):
     """Large-magnitude q.k (std ~ 40 in the log2 domain) so that block maxima jump by more than 2^16 and the lazy O rescale runs."""
     rel, mx = _run([1134, 640, 300], version, poly, seed=1, scale=3.0)
@@ -84,7 +84,7 @@ def test_attention_peaky_scores_exercise_rescale(version, poly):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("version", [4, 5, 6, 7])
+@pytest.mark.parametrize("version", [4, 5, 6, 7, 8])
 def test_attention_long_form(version):
     """configs[2]-like length (30 s + prompt): 23 key blocks, 12 query tiles per head."""
     rel, mx = _run([2856, 2584], version, 0, seed=2)
@@ -93,10 +93,11 @@ def test_attention_long_form(version):
 
 
 @pytest.mark.timeout(600)
-def test_attention_v6_persistent_many_items_per_cta():
+@pytest.mark.parametrize("version", [6, 8])
+def test_attention_persistent_many_items_per_cta(version):
     """More work items than SMs and very uneven ones (1-key, one-half, two-half tiles interleaved), so that every CTA of the
     persistent kernel crosses several item boundaries with different half counts and heads."""
     lens = [1134, 3, 700, 129, 1134, 64, 389, 257, 900, 1, 513, 1134, 200, 1100, 77, 640] * 2
-    rel, mx = _run(lens, 6, 3, seed=4)
-    print(f"attention v6 persistent, 32 ragged sequences: rel-L2 {rel:.3e}, max-abs {mx:.3e}")
+    rel, mx = _run(lens, version, 3, seed=4)
+    print(f"attention v{version} persistent, 32 ragged sequences: rel-L2 {rel:.3e}, max-abs {mx:.3e}")
     assert rel < 4e-3

@@ -19,6 +19,8 @@
 #include "attn5_tc.cuh"
 #include "attn6_tc.cuh"
 #include "attn7_tc.cuh"
+#include "attn8_tc.cuh"
+#include <algorithm>
 #include "conv_tc.cuh"
 #include "gemm_tc.cuh"
 #include "glue.cuh"
@@ -517,7 +519,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     else if (!strcmp(name, "gemm_2cta")) h->opt_gemm_2cta = value ? 1 : 0;
     else if (!strcmp(name, "gemm_mc")) h->opt_gemm_mc = value ? 1 : 0;
     else if (!strcmp(name, "attn_ptmem")) h->opt_attn_ptmem = value ? 1 : 0;
-    else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 7) return fail(TVB_ERR_INVALID, "attn_v must be 3 .. 7"); h->opt_attn_v = value; }
+    else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 8) return fail(TVB_ERR_INVALID, "attn_v must be 3 .. 8"); h->opt_attn_v = value; }
     else if (!strcmp(name, "attn_poly")) { if (value != 0 && value != 2 && value != 3 && value != 4 && !(value >= 100 && value < 108)) return fail(TVB_ERR_INVALID, "attn_poly must be 0, 2, 3 or 4"); h->opt_attn_poly = value; }
     else if (!strcmp(name, "ln_fuse")) h->opt_ln_fuse = value ? 1 : 0;
     else if (!strcmp(name, "profile")) { h->profile = value ? 1 : 0; h->ev_used = 0; h->ev_cat.clear(); }
@@ -582,6 +584,12 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
         for (int q0 = 0; q0 < len; q0 += 16) work16.push_back(make_int2(s, q0));
         for (int q0 = 0; q0 < len; q0 += ATT_BQ) work128.push_back(make_int4(s, q0, start, len));
     }
+    // heaviest query tiles first (cost ~ key blocks x query halves): the persistent attention kernel deals items round-robin,
+    // the non-persistent ones are scheduled in launch order, either way the short tiles fill the tail
+    std::stable_sort(work128.begin(), work128.end(), [](const int4& a, const int4& b) {
+        auto cost = [](const int4& w) { return ((w.w + ATT_BK - 1) / ATT_BK) * (w.y + 128 < w.w ? 2 : 1); };
+        return cost(a) > cost(b);
+    });
     // ---- workspace (re)allocation
     const bool bf = h->precision == TVB_PRECISION_BF16;
     const size_t state_n = static_cast<size_t>(B) * nf * T;
@@ -837,7 +845,9 @@ static int attention(tvb_handle* h, cudaStream_t st) {
     const int H = h->cfg.hidden_size, nh = h->cfg.num_attention_heads;
     ProfScope ps(h, st, PC_ATTN);
     // bf16 path: q carries head_dim^-0.5 * log2(e) (tvb_finalize_weights), so tensor-core scores are already in the log2 domain
-    if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 7) {
+    if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 8) {
+        CK(launch_attn8_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_poly, h->num_sms, st));
+    } else if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 7) {
         CK(launch_attn7_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_poly, st));
     } else if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 6) {
         CK(launch_attn6_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_poly, h->num_sms, st));
@@ -1130,6 +1140,10 @@ extern "C" int tvb_debug_attention(int device, const void* qkv_dev, void* ctx_de
         if (seq_len_host[s] <= 0 || seq_start_host[s] < 0 || seq_start_host[s] + seq_len_host[s] > rows) return fail(TVB_ERR_INVALID, "bad sequence %d", s);
         for (int q0 = 0; q0 < seq_len_host[s]; q0 += ATT_BQ) work.push_back(make_int4(s, q0, seq_start_host[s], seq_len_host[s]));
     }
+    std::stable_sort(work.begin(), work.end(), [](const int4& a, const int4& b) {
+        auto cost = [](const int4& w) { return ((w.w + ATT_BK - 1) / ATT_BK) * (w.y + 128 < w.w ? 2 : 1); };
+        return cost(a) > cost(b);
+    });
     int4* d_work = nullptr;
     CK(cudaMalloc(&d_work, work.size() * sizeof(int4)));
     CK(cudaMemcpyAsync(d_work, work.data(), work.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
@@ -1137,7 +1151,8 @@ extern "C" int tvb_debug_attention(int device, const void* qkv_dev, void* ctx_de
     int rc = make_tmap(&tm, qkv_dev, rows, 3 * H, 3 * H, 128);
     if (rc == TVB_OK) {
         cudaError_t e;
-        if (version == 7) e = launch_attn7_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, st);
+        if (version == 8) e = launch_attn8_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, prop.multiProcessorCount, st);
+        else if (version == 7) e = launch_attn7_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, st);
         else if (version == 6) e = launch_attn6_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, prop.multiProcessorCount, st);
         else if (version == 5) e = launch_attn5_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, st);
         else if (version == 4) e = launch_attn4_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, st);
