@@ -133,7 +133,7 @@ struct tvb_handle {
     int opt_gemm_mc = 0;        // CTA-pair GEMM: 1 = clusters of two pairs sharing the W tile by TMA multicast, 0 = independent pairs (default:
                                 // measured 7 % slower with multicast, profiles/r01: the pair kernel is not L2->SM bound after all)
     int opt_attn_ptmem = 1;     // tcgen05 attention v3: 1 = P kept in tensor memory (TS MMA), 0 = P staged through shared memory
-    int opt_attn_v = 7;         // tcgen05 attention kernel generation: 7 = attn7_tc.cuh (default), 6 / 5 / 4 = attnN_tc.cuh, 3 = attn_tc.cuh
+    int opt_attn_v = 8;         // tcgen05 attention kernel generation: 8 = attn8_tc.cuh (default), 7 .. 4 = attnN_tc.cuh, 3 = attn_tc.cuh
     int opt_attn_poly = 3;      // attention v4+: 0 = every exp2 on MUFU, n = one element pair in n on the FMA-pipe polynomial (default 3)
     int opt_ln_fuse = 1;        // bf16 path: 1 = LayerNorm writes bf16 + (mean, rstd) only and the residual GEMM epilogue re-normalises
                                 //            the fp32 stream on the fly (EPI_RESID_LN); 0 = LayerNorm materialises the fp32 result
