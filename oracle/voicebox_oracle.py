@@ -308,6 +308,26 @@ def generate(sd, cfg, x, cond, cond_lengths, n_timesteps, solver="euler", gradie
 
 
 # FLOP model of SURVEY.md §8(d): algorithmic FLOPs of one estimator call over valid tokens only.
+def cfm_forward_loss(sd, cfg, x, mask, x1, lengths, t=None, z=None, estimator=None):
+    """Training-loss forward, reference voicebox.py:28-49 (CFM.forward), no autograd.  t [B,1,1] ~ U(0,1) and z ~ N(0,1)
+    are drawn with the reference's call order (torch.rand then randn_like) unless given."""
+    if t is None:
+        t = torch.rand([x1.shape[0], 1, 1], device=x1.device, dtype=x1.dtype)
+    if z is None:
+        z = torch.randn_like(x1)
+    sigma_min = cfg["sigma_min"]
+    loss_mask = (torch.arange(0, x.shape[-1], device=lengths.device).unsqueeze(0) < lengths.unsqueeze(1)).float().unsqueeze(1)
+    y = (1 - (1 - sigma_min) * t) * z + t * x1
+    cond = x1 * mask
+    u = x1 - (1 - sigma_min) * z
+    est = estimator or (lambda x_, y_, c_, t_, l_: estimator_forward(sd, cfg, x_, y_, c_, t_.reshape(-1), l_))
+    ue = est(x, y, cond, t, lengths)
+    loss_mask = loss_mask * (1 - mask)
+    ue = ue * loss_mask
+    u = u * loss_mask
+    return F.mse_loss(ue, u, reduction="sum") / (torch.sum(loss_mask) * u.shape[1])
+
+
 def estimator_flops(token_counts: Sequence[int], cfg: Optional[dict] = None) -> float:
     cfg = cfg or DEFAULT_MODEL_CFG
     H, Fd, E, M = cfg["hidden_size"], cfg["intermediate_size"], cfg["embedding_dim"], cfg["n_feats"]

@@ -100,3 +100,31 @@ def test_edge_cases_zero_length_and_single_frame():
     assert float(v[0].abs().sum()) == 0.0 and float(v[1, :, 1:].abs().sum()) == 0.0
     with pytest.raises(ValueError):
         m.estimator(x.cuda(), y.cuda(), cond.cuda(), torch.tensor([0.2, 0.2, 0.2]), torch.tensor([0, 1, 33]))
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_cfm_forward_loss_value_vs_oracle(precision, tol):
+    """Voicebox.forward(x, mask, x1, lengths) = the reference's flow-matching loss (voicebox.py:28-49) with the same
+    RNG call order; per-sequence t goes through tvb_estimator_forward."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gen = torch.Generator().manual_seed(13)
+    B, T = 3, 150
+    x = torch.randint(0, 10000, (B, T), generator=gen).cuda()
+    x1 = torch.randn(B, 80, T, generator=gen).cuda()
+    L = torch.tensor([150, 90, 33]).cuda()
+    mask = torch.zeros(B, 80, T).cuda()
+    mask[0, :, 20:60] = 1                      # span-masked context frames (UnitMelBatchCollate, data_util.py:94-147)
+    mask[1, :, :30] = 1
+    sd = {k: v.cuda() for k, v in weights(0, True).items()}
+    m = model(0, True, precision)
+    torch.manual_seed(99)
+    got = m(x, mask, x1, L)
+    torch.manual_seed(99)
+    with torch.no_grad():
+        want = O.cfm_forward_loss(sd, CFG, x, mask, x1, L)
+    torch.cuda.synchronize()
+    rel = abs(float(got) - float(want)) / abs(float(want))
+    print(f"CFM.forward loss [{precision}]: {float(got):.6f} vs oracle {float(want):.6f} (rel {rel:.2e})")
+    assert got.dim() == 0 and torch.isfinite(got)
+    assert rel < tol

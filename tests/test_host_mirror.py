@@ -45,3 +45,22 @@ def test_load_state_dict_marks_weights_dirty():
     v0 = m._weights_version
     m.load_state_dict(m.state_dict())
     assert m._weights_version > v0
+
+
+def test_save_pretrained_from_pretrained_round_trip(tmp_path):
+    """the HF PyTorchModelHubMixin layout (config.json + model.safetensors) the reference publishes/loads
+    (voicebox.py:10,153; model_util.py:59-62) round-trips through the mirror with the reference's key names, offline."""
+    import usdm_b200
+    small = dict(CFG, num_hidden_layers=2)
+    torch.manual_seed(3)
+    m = usdm_b200.Voicebox(**small)
+    m.save_pretrained(str(tmp_path))
+    import os
+    assert os.path.exists(tmp_path / "model.safetensors")
+    m2 = usdm_b200.Voicebox.from_pretrained(str(tmp_path), **small)
+    sd, sd2 = m.state_dict(), m2.state_dict()
+    assert list(sd) == list(sd2)
+    for k in sd:
+        assert torch.equal(sd[k], sd2[k]), k
+    assert any(k.endswith("parametrizations.weight.original1") for k in sd)      # weight-norm keys as in the reference checkpoint
+    assert m2._weights_version > 0                                             # the engine will re-pack on first use

@@ -299,8 +299,25 @@ class Voicebox(nn.Module, PyTorchModelHubMixin):
             return self.solve_heun(x, z, cond, cond_lengths, t_span, gradient_scale, speech_prompt, prompt_lengths)
         # unknown solver: the reference silently returns None (voicebox.py:147-150)
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("training loss (CFM.forward, voicebox.py:28-49) is out of scope of the sampling engine")
+    # ---- CFM.forward (voicebox.py:28-49): flow-matching loss VALUE; the engine has no backward pass ---------
+    @torch.no_grad()
+    def forward(self, x, mask, x1, lengths):
+        """Same arguments, RNG call order (torch.rand for t, then randn_like for z) and arithmetic as the reference's
+        training forward; the velocity comes from the CUDA estimator.  Evaluation only: the result carries no autograd graph."""
+        if not x1.is_cuda:
+            raise RuntimeError("usdm_b200.Voicebox runs on CUDA tensors only (no CPU path); move inputs to the B200")
+        t = torch.rand([x1.shape[0], 1, 1], device=x1.device, dtype=x1.dtype)
+        z = torch.randn_like(x1)
+        lengths = torch.as_tensor(lengths).to(x1.device)
+        loss_mask = (torch.arange(0, x.shape[-1], device=lengths.device).unsqueeze(0) < lengths.unsqueeze(1)).float().unsqueeze(1)
+        y = (1 - (1 - self.sigma_min) * t) * z + t * x1
+        cond = x1 * mask
+        u = x1 - (1 - self.sigma_min) * z
+        ue = self.estimator(x, y, cond, t, lengths)
+        loss_mask = loss_mask * (1 - mask)
+        ue = ue * loss_mask
+        u = u * loss_mask
+        return torch.nn.functional.mse_loss(ue, u, reduction="sum") / (torch.sum(loss_mask) * u.shape[1])
 
     # ---- stats ---------------------------------------------------------------------------------------------
     def kernel_launches(self) -> int:
