@@ -286,8 +286,12 @@ def main():
         kernels = {k: dict(ms_per_step=v[0], launches=v[1]) for k, v in prof.items()}
         gemm_ms, gemm_n = prof["gemm"]
         achieved = fl["gemm"] * passes / (gemm_ms / 1e3) / 1e12
-        roof = dict(bound="tensor", kernel="gemm_tc_kernel (tcgen05 bf16 linear layers)", achieved=achieved, peak=peaks["sustained"],
-                    unit="TFLOP/s", frac=achieved / peaks["sustained"], traffic=None, peak_source=peaks["source"] + " bf16_tflops_sustained",
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")       # DRAM bytes per launch from the committed ncu --set full capture
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("avg_bytes_per_launch")
+        roof = dict(bound="tensor", kernel="gemm2_tc_kernel (tcgen05 bf16 linear layers, 108 launches per pass)", achieved=achieved, peak=peaks["sustained"],
+                    unit="TFLOP/s", frac=achieved / peaks["sustained"], traffic=traffic, peak_source=peaks["source"] + " bf16_tflops_sustained",
                     flops_per_launch=fl["gemm"] * passes / max(gemm_n, 1), avg_launch_ms=gemm_ms / max(gemm_n, 1),
                     share_of_step=gemm_ms / sum(v[0] for k, v in prof.items() if not k.startswith("gemm_")))
         for k in ("attention", "posconv"):
