@@ -298,7 +298,7 @@ def main():
             ms = prof[k][0]
             if ms > 0:
                 kernels[k]["tflops"] = fl[k] * passes / (ms / 1e3) / 1e12
-    step_tflops = fl["total"] * passes * args.steps / dev_s / 1e12
+    step_tflops = fl["total"] * passes * args.steps / dev_s / 1e12      # per GPU: fl counts this rank's batch, dev_s is the max over ranks
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
@@ -312,8 +312,8 @@ def main():
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(x_host.numel() * 8 + cond_host.numel() * 4),
                              d2h_bytes_per_step=int(out_host.numel() * 4), timing="wall clock, max over ranks"),
                     gpu_launches=int(launches), roofline=roof,
-                    roofline_step=dict(bound="tensor", achieved=step_tflops / world, peak=peaks["sustained"], unit="TFLOP/s per GPU",
-                                       frac=step_tflops / world / peaks["sustained"],
+                    roofline_step=dict(bound="tensor", achieved=step_tflops, peak=peaks["sustained"], unit="TFLOP/s per GPU",
+                                       frac=step_tflops / peaks["sustained"],
                                        note="algorithmic FLOPs of the whole solve (valid tokens) / device time"),
                     kernels=kernels, cpu_baseline=cpu)
         print(json.dumps(line), flush=True)
