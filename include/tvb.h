@@ -74,8 +74,8 @@ int tvb_get_precision(const tvb_handle* h);
  * "gemm_2cta" (1 = CTA-pair tcgen05 GEMM, default; 0 = single-CTA tcgen05 GEMM), "gemm_mc" (1 = two CTA pairs per cluster
  * sharing the W tile by TMA multicast; 0 = independent pairs, default), "attn_v" (8 = attn8_tc.cuh, 7 = attn7_tc.cuh, 6 = attn6_tc.cuh, 5 = attn5_tc.cuh, 4 = attn4_tc.cuh,
  * 3 = attn_tc.cuh), "attn_poly" (attention v4: 0 = every exp2 on MUFU; 2/3/4 = one element pair in n on the FMA-pipe
- * polynomial), "ln_fuse" (1 = LayerNorm re-applied in the residual GEMM epilogue instead of materialising the fp32
- * stream, default; 0 = separate fp32 LayerNorm output), and "profile" (see tvb_profile_read). */
+ * polynomial), "ln_fuse" (2 = LayerNorm computed inside the residual GEMM epilogue by 8-CTA clusters; 1 = LayerNorm
+ * kernel emits bf16 + row statistics and the residual GEMM epilogue re-normalises the fp32 stream; 0 = separate fp32 LayerNorm output), and "profile" (see tvb_profile_read). */
 int tvb_set_option(tvb_handle* h, const char* name, int32_t value);
 
 /* Replaces: Transformer.forward(x, y, cond, t, lengths) (networks.py:302-374) — the per-step velocity estimator.

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include "conv_tc.cuh"
 #include "gemm_tc.cuh"
+#include "gemmln_tc.cuh"
 #include "glue.cuh"
 #include "simt.cuh"
 
@@ -135,7 +136,8 @@ struct tvb_handle {
     int opt_attn_ptmem = 1;     // tcgen05 attention v3: 1 = P kept in tensor memory (TS MMA), 0 = P staged through shared memory
     int opt_attn_v = 8;         // tcgen05 attention kernel generation: 8 = attn8_tc.cuh (default), 7 .. 4 = attnN_tc.cuh, 3 = attn_tc.cuh
     int opt_attn_poly = 3;      // attention v4+: 0 = every exp2 on MUFU, n = one element pair in n on the FMA-pipe polynomial (default 3)
-    int opt_ln_fuse = 1;        // bf16 path: 1 = LayerNorm writes bf16 + (mean, rstd) only and the residual GEMM epilogue re-normalises
+    int opt_ln_fuse = 1;        // bf16 path: 2 = LayerNorm fused into the residual GEMM epilogue (8-CTA clusters, gemmln_tc.cuh);
+                                //            1 = LayerNorm writes bf16 + (mean, rstd) only and the residual GEMM epilogue re-normalises
                                 //            the fp32 stream on the fly (EPI_RESID_LN); 0 = LayerNorm materialises the fp32 result
     int profile = 0;            // 1: bracket every kernel with CUDA events on the launching stream (bench.py roofline leg)
     std::vector<cudaEvent_t> ev_pool;
@@ -521,7 +523,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     else if (!strcmp(name, "attn_ptmem")) h->opt_attn_ptmem = value ? 1 : 0;
     else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 8) return fail(TVB_ERR_INVALID, "attn_v must be 3 .. 8"); h->opt_attn_v = value; }
     else if (!strcmp(name, "attn_poly")) { if (value != 0 && value != 2 && value != 3 && value != 4 && !(value >= 100 && value < 108)) return fail(TVB_ERR_INVALID, "attn_poly must be 0, 2, 3 or 4"); h->opt_attn_poly = value; }
-    else if (!strcmp(name, "ln_fuse")) h->opt_ln_fuse = value ? 1 : 0;
+    else if (!strcmp(name, "ln_fuse")) { if (value < 0 || value > 2) return fail(TVB_ERR_INVALID, "ln_fuse must be 0, 1 or 2"); h->opt_ln_fuse = value; }
     else if (!strcmp(name, "profile")) { h->profile = value ? 1 : 0; h->ev_used = 0; h->ev_cat.clear(); }
     else return fail(TVB_ERR_INVALID, "unknown option %s", name);
     return TVB_OK;
@@ -776,6 +778,42 @@ static int launch_gemm2_tc(tvb_handle* h, int epi, const Gemm2Maps& maps, const 
     return fail(TVB_ERR_INVALID, "unknown epilogue %d", epi);
 }
 
+// out_f32 / out (bf16) = LayerNorm(a W^T + b + resid; g, beta): residual GEMM with the norm in its epilogue (bf16 path, N == 1024).
+static int linear_ln(tvb_handle* h, const Lin& lin, const Act& a, const float* resid, float* out_f32, Act* out, const float* g,
+                     const float* beta, cudaStream_t st, int cat) {
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+        CK(cudaFuncSetAttribute(gemmln_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM_BYTES));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(8 * 64);
+        cfg.blockDim = dim3(GL_THREADS);
+        cfg.dynamicSmemBytes = GL_SMEM_BYTES;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        CK(cudaOccupancyMaxActiveClusters(&n, gemmln_tc_kernel, &cfg));
+        if (n < 1) return fail(TVB_ERR_CUDA, "no 8-CTA cluster of the fused GEMM+LayerNorm kernel fits on this device");
+        max_clusters = n;
+    }
+    const int Mp = h->L.Mp;
+    if (lin.N != GL_N || Mp % 256 || lin.K % GEMM_BK) return fail(TVB_ERR_INVALID, "fused GEMM+LayerNorm needs N == 1024, M %% 256 == 0");
+    GemmLnMaps maps;
+    maps.a = a.tm; maps.b = lin.tm2;
+    maps.out = (out_f32 == h->xpre) ? h->tm_xpre : (out_f32 == h->xalt) ? h->tm_xalt : h->tm_hres;
+    maps.resid = (resid == h->xpre) ? h->tm_xpre : (resid == h->xalt) ? h->tm_xalt : h->tm_hres;
+    GemmLnParams p{};
+    p.M = Mp; p.K = lin.K; p.bias = lin.bias_tc; p.ln_g = g; p.ln_b = beta; p.eps = 1e-5f; p.out_bf16 = out->b16;
+    const int tiles = Mp / 256;
+    const int clusters = tiles < max_clusters ? tiles : max_clusters;
+    ProfScope ps(h, st, cat);
+    gemmln_tc_kernel<<<8 * clusters, GL_THREADS, GL_SMEM_BYTES, st>>>(maps, p);
+    h->launches++;
+    CKL();
+    return TVB_OK;
+}
+
 enum LinEpi { LE_PLAIN, LE_GELU, LE_RESID, LE_DUAL };
 // LayerNorm whose fp32 result is not materialised: rows of `x` with per-row (mean, rstd) in `stats` and the norm's affine.
 struct LnRef {
@@ -935,7 +973,8 @@ static int run_estimator(tvb_handle* h, const float* y, const float* t_seq_dev, 
     // ln_fuse (bf16 path): the fp32 post-LN stream is never written.  Each LayerNorm emits the bf16 GEMM operand and per-row
     // (mean, rstd); the residual GEMM that needs LayerNorm(x) in fp32 re-normalises x in its epilogue.  The pre-norm sums
     // ping-pong between xpre and xalt: O-proj reads xpre / writes xalt, FFN-out reads xalt / writes xpre.
-    const bool fuse = bf && h->opt_ln_fuse;
+    const bool epi_ln = bf && h->opt_ln_fuse == 2 && h->opt_gemm_2cta && H == GL_N;   // LayerNorm inside the residual GEMM epilogue
+    const bool fuse = bf && h->opt_ln_fuse && !epi_ln;
     LnRef cur_ln;                      // LayerNorm that produced the current layer input (valid when fuse && !plain_resid)
     bool plain_resid = !fuse;          // the current layer input exists as fp32 rows in hres
     if (fuse) {
@@ -958,7 +997,14 @@ static int run_estimator(tvb_handle* h, const float* y, const float* t_seq_dev, 
         TRY(linear(h, lw.qkv, *cur, nullptr, LE_PLAIN, &h->qkv, nullptr, nullptr, st, PC_GEMM_QKV));
         TRY(attention(h, st));
         const bool last = (l == nl - 1);
-        if (fuse) {
+        if (epi_ln) {
+            // hres holds the layer input (fp32, normalised); O-proj + LN1 -> xalt / hbB; FFN; FFN-out + LN2 -> hres / dst
+            TRY(linear_ln(h, lw.o, h->ctx, h->hres, h->xalt, &h->hbB, lw.ln1_g, lw.ln1_b, st, PC_GEMM_O));
+            TRY(linear(h, lw.f1, h->hbB, nullptr, LE_GELU, &h->mid, nullptr, nullptr, st, PC_GEMM_F1));
+            Act* dst = (l < nl / 2 - 1) ? &h->slots[sp++] : &h->hbA;
+            TRY(linear_ln(h, lw.f2, h->mid, h->xalt, h->hres, dst, lw.ln2_g, lw.ln2_b, st, PC_GEMM_F2));
+            cur = dst;
+        } else if (fuse) {
             // x1 = attn + (layer input) -> xalt ; LN1 -> hbB + statsB
             TRY(linear(h, lw.o, h->ctx, nullptr, LE_RESID, nullptr, h->hres, h->xalt, st, PC_GEMM_O, plain_resid ? nullptr : &cur_ln));
             TRY(layernorm(h, h->xalt, nullptr, &h->hbB, lw.ln1_g, lw.ln1_b, st, h->statsB));
