@@ -44,6 +44,8 @@ struct GemmParams {
     const float2* ln_stats;   // [M] (mean, rstd) of the resid rows            (EPI_RESID_LN)
     const float* ln_g;        // [N] LayerNorm weight / bias of the residual's norm
     const float* ln_b;
+    int reverse;              // CTA-pair kernels: walk the 256-row blocks from the last to the first.  Consumers traverse opposite to
+                              // the kernel that produced their input, so the rows they read first are the ones still in the 126 MB L2.
 };
 
 template <int EPI>
@@ -275,7 +277,11 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
     const int num_tiles = (p.M / (256 * NP)) * tiles_n;      // cluster tiles: NP vertically adjacent 256 x 256 tiles
     const int num_kb = p.K / GEMM_BK;
     const int cluster_id = blockIdx.x / (2 * NP), num_clusters = gridDim.x / (2 * NP);
-    auto tile_m0 = [&](int tile) { return ((tile / tiles_n) * NP + pair_id) * 256; };
+    const int m_blocks = p.M / (256 * NP);
+    auto tile_m0 = [&](int tile) {
+        const int mb = tile / tiles_n;
+        return ((p.reverse ? m_blocks - 1 - mb : mb) * NP + pair_id) * 256;
+    };
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tm.a); tma_prefetch_desc(&tm.a2); tma_prefetch_desc(&tm.b); tma_prefetch_desc(&tm.out);

@@ -12,7 +12,7 @@
 //   pass 1  thread == row: x for its 128 columns into registers (TMEM load + bias + residual tile staged by TMA), partial sums;
 //           the accumulator stage is released here already;
 //   xchg    every thread stores its partial into the statistics buffer of the 4 CTAs that hold the same rows (st.shared::cluster)
-//           and arrives (release.cluster) on their barrier; 4 CTAs x 256 threads arrivals complete a phase;
+//           and one lane per warp arrives (release.cluster) on their barrier; 4 CTAs x 8 warps arrivals complete a phase;
 //   pass 2  mean / rstd from the 8 partials, normalise from registers, fp32 tile -> swizzled staging -> TMA store, bf16 -> global.
 // On a 148-SM B200 16 such clusters are resident (128 SMs); the chip is power-capped in these GEMMs, so the
 // idle SMs cost clock headroom rather than throughput.
@@ -76,7 +76,7 @@ gemmln_tc_kernel(const __grid_constant__ GemmLnMaps tm, const GemmLnParams p) {
     uint64_t* empty_bar = full_bar + GL_STAGES;
     uint64_t* tfull_bar = empty_bar + GL_STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint64_t* stat_bar = tempty_bar + 2;                          // [2] by tile parity, 4 CTAs x 256 threads arrivals
+    uint64_t* stat_bar = tempty_bar + 2;                          // [2] by tile parity, 4 CTAs x 8 warps arrivals
     uint64_t* rbar = stat_bar + 2;                                // [8 warps][GL_EPI_BUFS] residual-tile arrival
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + GL_EPI_BUFS * G2_EPI_WARPS);
     float2* stat = reinterpret_cast<float2*>(smem + GL_SMEM_STAT);
@@ -96,7 +96,7 @@ gemmln_tc_kernel(const __grid_constant__ GemmLnMaps tm, const GemmLnParams p) {
     if (warp_idx == 1 && lane == 0) {
         for (int s = 0; s < GL_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * G2_EPI_WARPS); mbar_init(&stat_bar[s], 4 * G2_EPI_WARPS * 32);
+            mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * G2_EPI_WARPS); mbar_init(&stat_bar[s], 4 * G2_EPI_WARPS);
         }
         for (int s = 0; s < GL_EPI_BUFS * G2_EPI_WARPS; ++s) mbar_init(&rbar[s], 1);
         fence_barrier_init();
@@ -214,10 +214,13 @@ gemmln_tc_kernel(const __grid_constant__ GemmLnMaps tm, const GemmLnParams p) {
                 const uint32_t slot = stat_local + static_cast<uint32_t>((((as * 4 + pair_id) * 2 + chalf) * 128 + rloc) * 8);
                 const uint32_t sbar = statbar_local + static_cast<uint32_t>(as * 8);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t dst = static_cast<uint32_t>(2 * q) + cta;
-                    st_cluster_f32x2(mapa_u32(slot, dst), s1, s2);
-                    mbar_arrive_release_cluster(mapa_u32(sbar, dst));
+                for (int q = 0; q < 4; ++q) st_cluster_f32x2(mapa_u32(slot, static_cast<uint32_t>(2 * q) + cta), s1, s2);
+                // ONE arrival per warp and destination (1024 per-thread remote arrivals per tile serialised on the barrier and cost
+                // ~13 us per tile): the warp barrier orders the lanes' stores before lane 0's release.cluster arrive (cumulative)
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) mbar_arrive_release_cluster(mapa_u32(sbar, static_cast<uint32_t>(2 * q) + cta));
                 }
             }
             mbar_wait_acquire_cluster(&stat_bar[as], (it >> 1) & 1);

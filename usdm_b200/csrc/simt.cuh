@@ -118,12 +118,14 @@ k_frame_proj(RowLayout L, int T, int nf, int H, const float* __restrict__ Wt, co
 template <typename TB>
 __global__ void __launch_bounds__(256)
 k_layernorm(const float* __restrict__ x, float* __restrict__ y, TB* __restrict__ yb, const float* __restrict__ gamma,
-            const float* __restrict__ beta, const int* __restrict__ row_seq, int Mp, int H, float eps, float2* __restrict__ stats) {
+            const float* __restrict__ beta, const int* __restrict__ row_seq, int Mp, int H, float eps, float2* __restrict__ stats,
+            int reverse) {
     // y == nullptr (with stats != nullptr): the fp32 result is not materialised; consumers that need it (the residual add of
     // the next GEMM epilogue, EPI_RESID_LN) recompute it from x and the (mean, rstd) written to stats[row].
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int row_fwd = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (row >= Mp) return;
+    if (row_fwd >= Mp) return;
+    const int row = reverse ? Mp - 1 - row_fwd : row_fwd;      // reverse: start with the rows the producer wrote last (still in L2)
     const int nv = H / 128;                     // float4 per lane
     const bool valid = row_seq[row] >= 0;
     float4 v[8];

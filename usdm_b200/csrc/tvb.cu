@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -131,6 +132,7 @@ struct tvb_handle {
     int opt_attn_tc = 1;        // bf16 path: 1 = tcgen05 attention, 0 = CUDA-core attention (ablation / cross-check)
     int opt_conv_tc = 1;        // bf16 path: 1 = tcgen05 positional conv, 0 = CUDA-core conv
     int opt_gemm_2cta = 1;      // bf16 path: 1 = CTA-pair (cta_group::2) GEMM, 0 = single-CTA GEMM
+    int opt_zigzag = 1;         // bf16 path: row-block traversal alternates between producer and consumer kernels (L2 reuse)
     int opt_gemm_mc = 0;        // CTA-pair GEMM: 1 = clusters of two pairs sharing the W tile by TMA multicast, 0 = independent pairs (default:
                                 // measured 7 % slower with multicast, profiles/r01: the pair kernel is not L2->SM bound after all)
     int opt_attn_ptmem = 1;     // tcgen05 attention v3: 1 = P kept in tensor memory (TS MMA), 0 = P staged through shared memory
@@ -520,6 +522,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     else if (!strcmp(name, "conv_tc")) h->opt_conv_tc = value ? 1 : 0;
     else if (!strcmp(name, "gemm_2cta")) h->opt_gemm_2cta = value ? 1 : 0;
     else if (!strcmp(name, "gemm_mc")) h->opt_gemm_mc = value ? 1 : 0;
+    else if (!strcmp(name, "zigzag")) h->opt_zigzag = value ? 1 : 0;
     else if (!strcmp(name, "attn_ptmem")) h->opt_attn_ptmem = value ? 1 : 0;
     else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 8) return fail(TVB_ERR_INVALID, "attn_v must be 3 .. 8"); h->opt_attn_v = value; }
     else if (!strcmp(name, "attn_poly")) { if (value != 0 && value != 2 && value != 3 && value != 4 && !(value >= 100 && value < 108)) return fail(TVB_ERR_INVALID, "attn_poly must be 0, 2, 3 or 4"); h->opt_attn_poly = value; }
@@ -742,6 +745,7 @@ static int launch_gemm4_tc_t(tvb_handle* h, const Gemm2Maps& maps, const GemmPar
         CK(cudaOccupancyMaxActiveClusters(&n, gemm4_tc_kernel<EPI>, &cfg));
         if (n < 1) return fail(TVB_ERR_CUDA, "no 4-CTA cluster fits on this device");
         max_clusters = n;
+        if (getenv("TVB_DEBUG")) fprintf(stderr, "[tvb] gemm4_tc_kernel: %d resident 4-CTA clusters\n", n);
     }
     const int tiles = (p.M / 512) * (p.N / 256);
     const int clusters = tiles < max_clusters ? tiles : max_clusters;
@@ -796,6 +800,7 @@ static int linear_ln(tvb_handle* h, const Lin& lin, const Act& a, const float* r
         CK(cudaOccupancyMaxActiveClusters(&n, gemmln_tc_kernel, &cfg));
         if (n < 1) return fail(TVB_ERR_CUDA, "no 8-CTA cluster of the fused GEMM+LayerNorm kernel fits on this device");
         max_clusters = n;
+        if (getenv("TVB_DEBUG")) fprintf(stderr, "[tvb] gemmln_tc_kernel: %d resident 8-CTA clusters\n", n);
     }
     const int Mp = h->L.Mp;
     if (lin.N != GL_N || Mp % 256 || lin.K % GEMM_BK) return fail(TVB_ERR_INVALID, "fused GEMM+LayerNorm needs N == 1024, M %% 256 == 0");
@@ -829,13 +834,14 @@ static const CUtensorMap& f32_map(tvb_handle* h, const float* ptr) {
 //   LE_RESID: -> + resid -> out_f32 (resid = fp32 rows, or LayerNorm(ln->x) re-normalised in the epilogue when ln != nullptr)
 //   LE_DUAL:  -> out_f32 and out (Act)
 static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, LinEpi epi, Act* out, const float* resid, float* out_f32,
-                  cudaStream_t st, int cat = PC_GEMM, const LnRef* ln = nullptr) {
+                  cudaStream_t st, int cat = PC_GEMM, const LnRef* ln = nullptr, bool rev = false) {
     const int Mp = h->L.Mp;
     if (h->precision == TVB_PRECISION_BF16) {
         GemmParams p{};
         p.M = Mp; p.N = lin.N; p.K = lin.K; p.K1 = a2 ? a.C : lin.K;
         p.bias = lin.bias_tc; p.resid = ln ? ln->x : resid; p.out_f32 = out_f32; p.out_bf16 = out ? out->b16 : nullptr; p.ld_out = lin.N;
         if (ln) { p.ln_stats = ln->stats; p.ln_g = ln->g; p.ln_b = ln->b; }
+        p.reverse = (rev && h->opt_zigzag) ? 1 : 0;
         const int e = epi == LE_PLAIN ? EPI_BF16 : epi == LE_GELU ? EPI_GELU_BF16 : epi == LE_RESID ? (ln ? EPI_RESID_LN : EPI_RESID_F32) : EPI_DUAL;
         if (h->opt_gemm_2cta) {
             Gemm2Maps maps;
@@ -867,13 +873,13 @@ static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, Li
 
 // y (fp32, may be nullptr when stats != nullptr) and yb (operand copy in the active precision) = LayerNorm(x); eps 1e-5.
 static int layernorm(tvb_handle* h, const float* x, float* y, Act* yb, const float* g, const float* b, cudaStream_t st,
-                     float2* stats = nullptr) {
+                     float2* stats = nullptr, bool rev = false) {
     const int Mp = h->L.Mp, H = h->cfg.hidden_size;
     ProfScope ps(h, st, PC_NORM);
     if (h->precision == TVB_PRECISION_BF16)
-        k_layernorm<bf16><<<(Mp + 7) / 8, 256, 0, st>>>(x, y, yb ? yb->b16 : nullptr, g, b, h->L.row_seq, Mp, H, 1e-5f, stats);
+        k_layernorm<bf16><<<(Mp + 7) / 8, 256, 0, st>>>(x, y, yb ? yb->b16 : nullptr, g, b, h->L.row_seq, Mp, H, 1e-5f, stats, (rev && h->opt_zigzag) ? 1 : 0);
     else
-        k_layernorm<float><<<(Mp + 7) / 8, 256, 0, st>>>(x, y, yb ? yb->f32 : nullptr, g, b, h->L.row_seq, Mp, H, 1e-5f, stats);
+        k_layernorm<float><<<(Mp + 7) / 8, 256, 0, st>>>(x, y, yb ? yb->f32 : nullptr, g, b, h->L.row_seq, Mp, H, 1e-5f, stats, 0);
     h->launches++;
     CKL();
     return TVB_OK;
@@ -978,7 +984,7 @@ static int run_estimator(tvb_handle* h, const float* y, const float* t_seq_dev, 
     LnRef cur_ln;                      // LayerNorm that produced the current layer input (valid when fuse && !plain_resid)
     bool plain_resid = !fuse;          // the current layer input exists as fp32 rows in hres
     if (fuse) {
-        TRY(layernorm(h, h->xpre, nullptr, &h->slots[0], h->ln0_g, h->ln0_b, st, h->statsA));
+        TRY(layernorm(h, h->xpre, nullptr, &h->slots[0], h->ln0_g, h->ln0_b, st, h->statsA, true));
         cur_ln.x = h->xpre; cur_ln.stats = h->statsA; cur_ln.g = h->ln0_g; cur_ln.b = h->ln0_b;
     } else {
         TRY(layernorm(h, h->xpre, h->hres, &h->slots[0], h->ln0_g, h->ln0_b, st));
@@ -990,11 +996,13 @@ static int run_estimator(tvb_handle* h, const float* y, const float* t_seq_dev, 
         const LayerW& lw = h->layers[l];
         if (l >= nl / 2) {            // U-Net merge: Linear(2H -> H)([h ; skip]) as a two-operand split-K GEMM (networks.py:361-363)
             const Act* skip = &h->slots[--sp];
-            TRY(linear(h, h->skip[l - nl / 2], *cur, skip, LE_DUAL, &h->hbB, nullptr, h->hres, st, PC_GEMM_SKIP));
+            // traversal directions (zigzag): LayerNorms that feed a layer run last-row-first, so the consumer of their output
+            // (skip merge or QKV) runs first-row-first; a QKV fed by the skip merge runs last-row-first
+            TRY(linear(h, h->skip[l - nl / 2], *cur, skip, LE_DUAL, &h->hbB, nullptr, h->hres, st, PC_GEMM_SKIP, nullptr, false));
             cur = &h->hbB;
             plain_resid = true;
         }
-        TRY(linear(h, lw.qkv, *cur, nullptr, LE_PLAIN, &h->qkv, nullptr, nullptr, st, PC_GEMM_QKV));
+        TRY(linear(h, lw.qkv, *cur, nullptr, LE_PLAIN, &h->qkv, nullptr, nullptr, st, PC_GEMM_QKV, nullptr, l >= nl / 2));
         TRY(attention(h, st));
         const bool last = (l == nl - 1);
         if (epi_ln) {
@@ -1006,15 +1014,16 @@ static int run_estimator(tvb_handle* h, const float* y, const float* t_seq_dev, 
             cur = dst;
         } else if (fuse) {
             // x1 = attn + (layer input) -> xalt ; LN1 -> hbB + statsB
-            TRY(linear(h, lw.o, h->ctx, nullptr, LE_RESID, nullptr, h->hres, h->xalt, st, PC_GEMM_O, plain_resid ? nullptr : &cur_ln));
-            TRY(layernorm(h, h->xalt, nullptr, &h->hbB, lw.ln1_g, lw.ln1_b, st, h->statsB));
-            TRY(linear(h, lw.f1, h->hbB, nullptr, LE_GELU, &h->mid, nullptr, nullptr, st, PC_GEMM_F1));
+            // attention wrote ctx first-row-first: O-proj walks back (rev), LN1 forward, FFN-in back, FFN-out forward, LN2 back
+            TRY(linear(h, lw.o, h->ctx, nullptr, LE_RESID, nullptr, h->hres, h->xalt, st, PC_GEMM_O, plain_resid ? nullptr : &cur_ln, true));
+            TRY(layernorm(h, h->xalt, nullptr, &h->hbB, lw.ln1_g, lw.ln1_b, st, h->statsB, false));
+            TRY(linear(h, lw.f1, h->hbB, nullptr, LE_GELU, &h->mid, nullptr, nullptr, st, PC_GEMM_F1, nullptr, true));
             LnRef ln1;
             ln1.x = h->xalt; ln1.stats = h->statsB; ln1.g = lw.ln1_g; ln1.b = lw.ln1_b;
-            TRY(linear(h, lw.f2, h->mid, nullptr, LE_RESID, nullptr, nullptr, h->xpre, st, PC_GEMM_F2, &ln1));
+            TRY(linear(h, lw.f2, h->mid, nullptr, LE_RESID, nullptr, nullptr, h->xpre, st, PC_GEMM_F2, &ln1, false));
             Act* dst = (l < nl / 2 - 1) ? &h->slots[sp++] : &h->hbA;
             // the last layer's output feeds the fp32 output projection: materialise it
-            TRY(layernorm(h, h->xpre, last ? h->hres : nullptr, dst, lw.ln2_g, lw.ln2_b, st, h->statsA));
+            TRY(layernorm(h, h->xpre, last ? h->hres : nullptr, dst, lw.ln2_g, lw.ln2_b, st, h->statsA, true));
             cur_ln.x = h->xpre; cur_ln.stats = h->statsA; cur_ln.g = lw.ln2_g; cur_ln.b = lw.ln2_b;
             plain_resid = false;
             cur = dst;
