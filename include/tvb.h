@@ -75,7 +75,9 @@ int tvb_get_precision(const tvb_handle* h);
  * sharing the W tile by TMA multicast; 0 = independent pairs, default), "attn_v" (8 = attn8_tc.cuh, 7 = attn7_tc.cuh, 6 = attn6_tc.cuh, 5 = attn5_tc.cuh, 4 = attn4_tc.cuh,
  * 3 = attn_tc.cuh), "attn_poly" (attention v4: 0 = every exp2 on MUFU; 2/3/4 = one element pair in n on the FMA-pipe
  * polynomial), "ln_fuse" (2 = LayerNorm computed inside the residual GEMM epilogue by 8-CTA clusters; 1 = LayerNorm
- * kernel emits bf16 + row statistics and the residual GEMM epilogue re-normalises the fp32 stream; 0 = separate fp32 LayerNorm output), and "profile" (see tvb_profile_read). */
+ * kernel emits bf16 + row statistics and the residual GEMM epilogue re-normalises the fp32 stream; 0 = separate fp32 LayerNorm output), "ln1_fold" (with ln_fuse = 1: 1 = the LayerNorm between attention and FFN is folded into the FFN-in GEMM, default;
+ * 0 = it runs as a kernel), "zigzag" (1 = producer / consumer kernels walk the rows in opposite directions for L2 reuse,
+ * default), and "profile" (see tvb_profile_read). */
 int tvb_set_option(tvb_handle* h, const char* name, int32_t value);
 
 /* Replaces: Transformer.forward(x, y, cond, t, lengths) (networks.py:302-374) — the per-step velocity estimator.

@@ -45,6 +45,8 @@ def model(seed=0, perturb=False, precision="bf16"):
     m.set_option("attn_v", 8)
     m.set_option("attn_poly", 3)
     m.set_option("ln_fuse", 1)
+    m.set_option("ln1_fold", 1)
+    m.set_option("zigzag", 1)
     return m
 
 

@@ -31,6 +31,12 @@ enum GemmEpilogue : int {
     EPI_F32 = 4,         // out_f32  = acc + bias
     EPI_RESID_LN = 5,    // out_f32  = acc + bias + LayerNorm(resid)  with per-row (mean, rstd) from ln_stats and per-column ln_g / ln_b:
                          // the post-LN residual stream is re-normalised on the fly instead of being written and re-read in fp32
+    // LayerNorm folded into the NEXT GEMM (N == 1024 producers only): the residual epilogue also emits a bf16 copy of its
+    // un-normalised result and per-row partial (sum, sum of squares) per 128-column slice; the consumer multiplies the raw rows
+    // with W diag(gamma) and applies  rstd * acc - rstd * mean * colsum(W diag(gamma)) + (b + W beta)  in its epilogue.
+    EPI_RESID_F32_ST = 6,   // EPI_RESID_F32 + bf16 copy + partial statistics
+    EPI_RESID_LN_ST = 7,    // EPI_RESID_LN  + bf16 copy + partial statistics
+    EPI_FOLD_GELU = 8,      // out_bf16 = gelu(rstd * acc - rstd * mean * fold_c + bias)  (bias already holds b + W beta)
 };
 
 struct GemmParams {
@@ -44,6 +50,9 @@ struct GemmParams {
     const float2* ln_stats;   // [M] (mean, rstd) of the resid rows            (EPI_RESID_LN)
     const float* ln_g;        // [N] LayerNorm weight / bias of the residual's norm
     const float* ln_b;
+    float2* part;             // [M, 8] per-row partial (sum, sum of squares) over columns [128 q, 128 q + 128)   (*_ST write, FOLD reads)
+    const float* fold_c;      // [N] column sums of the folded weight                                              (EPI_FOLD_GELU)
+    float2* stats_out;        // [M] (mean, rstd), written once per row by the n == 0 tiles                        (EPI_FOLD_GELU)
     int reverse;              // CTA-pair kernels: walk the 256-row blocks from the last to the first.  Consumers traverse opposite to
                               // the kernel that produced their input, so the rows they read first are the ones still in the 126 MB L2.
 };
@@ -239,7 +248,7 @@ constexpr int G2_B_BYTES = 128 * GEMM_BK * 2;                // 16 KB (this CTA'
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 constexpr int G2_EPI_WARPS = 8;
 constexpr int G2_EPI_TILE = 4096;                            // 32 rows x 128 B
-constexpr int G2_EPI_BUFS = 3;                               // staging tiles per epilogue warp: computing / residual in flight / storing
+constexpr int G2_EPI_BUFS = 2;                               // staging tiles per epilogue warp (a third one measured no gain)
 constexpr int G2_SMEM_EPI = G2_STAGES * G2_STAGE_BYTES;
 constexpr int G2_SMEM_BAR = G2_SMEM_EPI + G2_EPI_WARPS * G2_EPI_BUFS * G2_EPI_TILE;
 constexpr int G2_SMEM_BYTES = G2_SMEM_BAR + 1024 + 512;
@@ -285,7 +294,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tm.a); tma_prefetch_desc(&tm.a2); tma_prefetch_desc(&tm.b); tma_prefetch_desc(&tm.out);
-        if (EPI == EPI_RESID_F32 || EPI == EPI_RESID_LN) tma_prefetch_desc(&tm.resid);
+        if (EPI == EPI_RESID_F32 || EPI == EPI_RESID_LN || EPI == EPI_RESID_F32_ST || EPI == EPI_RESID_LN_ST) tma_prefetch_desc(&tm.resid);
     }
     if (warp_idx == 1 && lane == 0) {
         for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NP); }
@@ -347,8 +356,11 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
         }
     } else {
         // ------------------------------------------ epilogue ------------------------------------------
-        constexpr bool kBf16Out = (EPI == EPI_BF16 || EPI == EPI_GELU_BF16);
-        constexpr bool kResid = (EPI == EPI_RESID_F32 || EPI == EPI_RESID_LN);
+        constexpr bool kBf16Out = (EPI == EPI_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_FOLD_GELU);
+        constexpr bool kStats = (EPI == EPI_RESID_F32_ST || EPI == EPI_RESID_LN_ST);
+        constexpr bool kResidPlain = (EPI == EPI_RESID_F32 || EPI == EPI_RESID_F32_ST);
+        constexpr bool kResidLn = (EPI == EPI_RESID_LN || EPI == EPI_RESID_LN_ST);
+        constexpr bool kResid = kResidPlain || kResidLn;
         constexpr int kChunkCols = kBf16Out ? 64 : 32;            // one staging tile row = 128 B
         constexpr int kChunks = 128 / kChunkCols;                 // per warp per tile
         const int ew = warp_idx - 2;
@@ -378,6 +390,22 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
             mbar_wait(&tfull_bar[as], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256 + chalf * 128;
+            float ps1 = 0.f, ps2 = 0.f;                               // *_ST: this thread's partial row statistics over its 128 columns
+            float fa = 1.f, fb = 0.f;                                 // FOLD: rstd and -rstd * mean of this thread's row
+            if constexpr (EPI == EPI_FOLD_GELU) {
+                const int frow = tile_m0(tile) + static_cast<int>(cta) * 128 + quad * 32 + lane;
+                const float4* pp = reinterpret_cast<const float4*>(p.part + static_cast<size_t>(frow) * 8);
+                float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 a = pp[q];
+                    t1 += a.x + a.z; t2 += a.y + a.w;
+                }
+                const float mean = t1 * (1.0f / 1024.0f);
+                const float rstd = rsqrtf(fmaxf(t2 * (1.0f / 1024.0f) - mean * mean, 0.f) + 1e-5f);
+                fa = rstd; fb = -rstd * mean;
+                if ((tile % tiles_n) == 0 && chalf == 0) p.stats_out[frow] = make_float2(mean, rstd);
+            }
 #pragma unroll 1
             for (int c = 0; c < kChunks; ++c, ++kc) {
                 uint8_t* tile_s = stg + buf * G2_EPI_TILE;
@@ -411,7 +439,16 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[q * 32 + j] = __uint_as_float(r[j]);
                 }
-                if (p.bias != nullptr) {
+                if constexpr (EPI == EPI_FOLD_GELU) {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+                    const float4* c4 = reinterpret_cast<const float4*>(p.fold_c + col);
+#pragma unroll
+                    for (int j = 0; j < kChunkCols / 4; ++j) {
+                        const float4 b = __ldg(b4 + j), cc = __ldg(c4 + j);
+                        v[4 * j + 0] = fmaf(fa, v[4 * j + 0], fmaf(fb, cc.x, b.x)); v[4 * j + 1] = fmaf(fa, v[4 * j + 1], fmaf(fb, cc.y, b.y));
+                        v[4 * j + 2] = fmaf(fa, v[4 * j + 2], fmaf(fb, cc.z, b.z)); v[4 * j + 3] = fmaf(fa, v[4 * j + 3], fmaf(fb, cc.w, b.w));
+                    }
+                } else if (p.bias != nullptr) {
                     const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
                     for (int j = 0; j < kChunkCols / 4; ++j) {
@@ -419,30 +456,38 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                         v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
                     }
                 }
-                if constexpr (EPI == EPI_GELU_BF16) {
+                if constexpr (EPI == EPI_GELU_BF16 || EPI == EPI_FOLD_GELU) {
 #pragma unroll
                     for (int j = 0; j < kChunkCols; ++j) v[j] = gelu_erf_fast(v[j]);
                 }
                 uint8_t* rowp = tile_s + lane * 128;               // this thread's row of the staging tile
-                if constexpr (EPI == EPI_RESID_F32) {
+                if constexpr (kResid) {
+                    float2 st = make_float2(0.f, 1.f);
+                    if constexpr (kResidLn) st = p.ln_stats[row + lane];      // (mean, rstd) of this thread's residual row
+                    const float4* g4 = reinterpret_cast<const float4*>(p.ln_g + col);
+                    const float4* b4 = reinterpret_cast<const float4*>(p.ln_b + col);
                     mbar_wait(&rb[buf], bpar);                     // residual tile landed (async proxy -> visible after wait)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4* q4 = reinterpret_cast<float4*>(rowp + ((j ^ r7) << 4));
                         const float4 rr = *q4;
-                        *q4 = make_float4(v[4 * j] + rr.x, v[4 * j + 1] + rr.y, v[4 * j + 2] + rr.z, v[4 * j + 3] + rr.w);
+                        if constexpr (kResidLn) {
+                            const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
+                            v[4 * j] += fmaf((rr.x - st.x) * st.y, g.x, b.x); v[4 * j + 1] += fmaf((rr.y - st.x) * st.y, g.y, b.y);
+                            v[4 * j + 2] += fmaf((rr.z - st.x) * st.y, g.z, b.z); v[4 * j + 3] += fmaf((rr.w - st.x) * st.y, g.w, b.w);
+                        } else {
+                            v[4 * j] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
+                        }
+                        *q4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     }
-                } else if constexpr (EPI == EPI_RESID_LN) {
-                    const float2 st = p.ln_stats[row + lane];      // (mean, rstd) of this thread's residual row
-                    const float4* g4 = reinterpret_cast<const float4*>(p.ln_g + col);
-                    const float4* b4 = reinterpret_cast<const float4*>(p.ln_b + col);
-                    mbar_wait(&rb[buf], bpar);
+                    if constexpr (kStats) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4* q4 = reinterpret_cast<float4*>(rowp + ((j ^ r7) << 4));
-                        const float4 rr = *q4, g = __ldg(g4 + j), b = __ldg(b4 + j);
-                        *q4 = make_float4(v[4 * j] + fmaf((rr.x - st.x) * st.y, g.x, b.x), v[4 * j + 1] + fmaf((rr.y - st.x) * st.y, g.y, b.y),
-                                          v[4 * j + 2] + fmaf((rr.z - st.x) * st.y, g.z, b.z), v[4 * j + 3] + fmaf((rr.w - st.x) * st.y, g.w, b.w));
+                        for (int j = 0; j < 32; ++j) { ps1 += v[j]; ps2 = fmaf(v[j], v[j], ps2); }
+                        uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(row + lane) * p.ld_out + col);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
                     }
                 } else if constexpr (kBf16Out) {
 #pragma unroll
@@ -470,6 +515,9 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                 }
                 if (++buf == G2_EPI_BUFS) { buf = 0; bpar ^= 1; }
             }
+            if constexpr (kStats)
+                p.part[static_cast<size_t>(tile_m0(tile) + static_cast<int>(cta) * 128 + quad * 32 + lane) * 8 + (tile % tiles_n) * 2 + chalf] =
+                    make_float2(ps1, ps2);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], static_cast<uint32_t>(2 * pair_id));   // the pair leader's MMA thread owns accumulator reuse

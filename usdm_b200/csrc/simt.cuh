@@ -438,6 +438,27 @@ k_ode_update(const float* __restrict__ vbuf, int ldv, RowLayout L, OdeParams p) 
 // ------------------------------------------------------------------------------------------------------------
 // Weight packing kernels (run once in tvb_finalize_weights)
 // ------------------------------------------------------------------------------------------------------------
+// ---- LayerNorm folding (tvb_finalize_weights): W' = W diag(gamma) ; c[n] = sum_k bf16(W'[n,k]) ; b'[n] = b[n] + sum_k W[n,k] beta[k]
+__global__ void k_fold_cols(const float* __restrict__ W, const float* __restrict__ gamma, float* __restrict__ out, int N, int K) {
+    const size_t n = static_cast<size_t>(N) * K;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        out[i] = W[i] * gamma[i % K];
+}
+// one warp per output row
+__global__ void k_fold_rows(const float* __restrict__ W, const __nv_bfloat16* __restrict__ Wf16, const float* __restrict__ beta,
+                            const float* __restrict__ bias, float* __restrict__ c_out, float* __restrict__ b_out, int N, int K) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= N) return;
+    float c = 0.f, b = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        c += __bfloat162float(Wf16[static_cast<size_t>(row) * K + k]);
+        b = fmaf(W[static_cast<size_t>(row) * K + k], beta[k], b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if (lane == 0) { c_out[row] = c; b_out[row] = bias[row] + b; }
+}
 __global__ void k_f32_to_bf16(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
         out[i] = __float2bfloat16_rn(in[i]);

@@ -103,6 +103,7 @@ struct Lin {                 // one nn.Linear: y = x W^T + b
     bf16* w16 = nullptr;
     const float* bias = nullptr;
     const float* bias_tc = nullptr;   // bias of the bf16 tensor-core path (differs from `bias` only for the fused QKV projection)
+    const float* fold_c = nullptr;    // column sums of a LayerNorm-folded weight (EPI_FOLD_GELU)
     int N = 0, K = 0;
     CUtensorMap tm;          // B operand map: [N, K], box 256 x 64 (single-CTA kernel)
     CUtensorMap tm2;         // B operand map: [N, K], box 128 x 64 (CTA-pair kernel: each CTA stages half of the W tile)
@@ -117,6 +118,8 @@ struct Act {                 // an activation buffer [Mp, C] in the precision of
 };
 struct LayerW {
     Lin qkv, o, f1, f2;
+    Lin f1_fold;                       // FFN-in with LN1 folded in: W1 diag(gamma1) in bf16, bias_tc = b1 + W1 beta1
+    float* f1_fold_c = nullptr;        // [F] column sums of the folded bf16 weight
     const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
 };
 
@@ -132,6 +135,8 @@ struct tvb_handle {
     int opt_attn_tc = 1;        // bf16 path: 1 = tcgen05 attention, 0 = CUDA-core attention (ablation / cross-check)
     int opt_conv_tc = 1;        // bf16 path: 1 = tcgen05 positional conv, 0 = CUDA-core conv
     int opt_gemm_2cta = 1;      // bf16 path: 1 = CTA-pair (cta_group::2) GEMM, 0 = single-CTA GEMM
+    int opt_ln1_fold = 1;       // bf16 path with ln_fuse == 1: LN1 folded into the FFN-in GEMM (no LN1 kernel, attention-out epilogue emits
+                                // a bf16 copy + row statistics); 0 = LN1 as a kernel
     int opt_zigzag = 1;         // bf16 path: row-block traversal alternates between producer and consumer kernels (L2 reuse)
     int opt_gemm_mc = 0;        // CTA-pair GEMM: 1 = clusters of two pairs sharing the W tile by TMA multicast, 0 = independent pairs (default:
                                 // measured 7 % slower with multicast, profiles/r01: the pair kernel is not L2->SM bound after all)
@@ -175,6 +180,7 @@ struct tvb_handle {
     Act hin, p1, slots[32], hbA, hbB, qkv, ctx, mid;
     float *xpre = nullptr, *xalt = nullptr, *hres = nullptr, *vbuf = nullptr;
     float2 *statsA = nullptr, *statsB = nullptr;       // per-row (mean, rstd) of the two LayerNorms in flight (ln_fuse)
+    float2* ln_part = nullptr;                         // [Mp, 8] partial row statistics (ln1_fold)
     float *z_work = nullptr, *z_hat = nullptr, *v_pred = nullptr;
     CUtensorMap tm_xpre, tm_xalt, tm_hres;       // fp32 [Mp, H] epilogue maps (box 32 rows x 32 columns): TMA store / residual load
 };
@@ -427,7 +433,7 @@ extern "C" int tvb_finalize_weights(tvb_handle* h) {
     // encoder layers
     h->layers.resize(nl);
     float* wqkv_tc = nullptr;                                  // scratch, reused by every layer (stream-ordered), freed below
-    CK(cudaMalloc(&wqkv_tc, 3 * static_cast<size_t>(H) * H * sizeof(float)));
+    CK(cudaMalloc(&wqkv_tc, (3 * static_cast<size_t>(H) > static_cast<size_t>(F) ? 3 * static_cast<size_t>(H) : static_cast<size_t>(F)) * H * sizeof(float)));
     for (int l = 0; l < nl; ++l) {
         const std::string lp = p + "layers." + std::to_string(l) + ".";
         const float *wq, *wk, *wv, *bq, *bk, *bv, *wo, *bo, *w1, *b1, *w2, *b2;
@@ -470,6 +476,17 @@ extern "C" int tvb_finalize_weights(tvb_handle* h) {
         TRY(make_lin(h, &lw.o, wo, bo, H, H));
         TRY(make_lin(h, &lw.f1, w1, b1, F, H));
         TRY(make_lin(h, &lw.f2, w2, b2, H, F));
+        {   // LN1 folded into FFN-in (bf16 path, option ln1_fold): see gemm_tc.cuh EPI_FOLD_GELU
+            float* bfold = nullptr;
+            TRY(dev_alloc_t(h, h->owned, &bfold, static_cast<size_t>(F)));
+            TRY(dev_alloc_t(h, h->owned, &lw.f1_fold_c, static_cast<size_t>(F)));
+            k_fold_cols<<<grid_for(static_cast<size_t>(F) * H), 256>>>(w1, lw.ln1_g, wqkv_tc, F, H);     // scratch holds 3 H^2 >= F H floats? checked below
+            CKL();
+            TRY(make_lin(h, &lw.f1_fold, w1, b1, F, H, wqkv_tc, bfold));
+            k_fold_rows<<<(F + 7) / 8, 256>>>(w1, lw.f1_fold.w16, lw.ln1_b, b1, lw.f1_fold_c, bfold, F, H);
+            CKL();
+            lw.f1_fold.fold_c = lw.f1_fold_c;
+        }
     }
     h->skip.resize(nl / 2);
     for (int m = 0; m < nl / 2; ++m) {
@@ -523,6 +540,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     else if (!strcmp(name, "gemm_2cta")) h->opt_gemm_2cta = value ? 1 : 0;
     else if (!strcmp(name, "gemm_mc")) h->opt_gemm_mc = value ? 1 : 0;
     else if (!strcmp(name, "zigzag")) h->opt_zigzag = value ? 1 : 0;
+    else if (!strcmp(name, "ln1_fold")) h->opt_ln1_fold = value ? 1 : 0;
     else if (!strcmp(name, "attn_ptmem")) h->opt_attn_ptmem = value ? 1 : 0;
     else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 8) return fail(TVB_ERR_INVALID, "attn_v must be 3 .. 8"); h->opt_attn_v = value; }
     else if (!strcmp(name, "attn_poly")) { if (value != 0 && value != 2 && value != 3 && value != 4 && !(value >= 100 && value < 108)) return fail(TVB_ERR_INVALID, "attn_poly must be 0, 2, 3 or 4"); h->opt_attn_poly = value; }
@@ -621,6 +639,7 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
         TRY(alloc_f32(h, &h->xalt, static_cast<size_t>(rows) * H));
         TRY(alloc_f32(h, reinterpret_cast<float**>(&h->statsA), 2 * static_cast<size_t>(rows)));
         TRY(alloc_f32(h, reinterpret_cast<float**>(&h->statsB), 2 * static_cast<size_t>(rows)));
+        TRY(alloc_f32(h, reinterpret_cast<float**>(&h->ln_part), 16 * static_cast<size_t>(rows)));
         TRY(alloc_f32(h, &h->hres, static_cast<size_t>(rows) * H));
         TRY(alloc_f32(h, &h->vbuf, static_cast<size_t>(rows) * nf));
         TRY(alloc_f32(h, &h->z_work, sn));
@@ -778,6 +797,9 @@ static int launch_gemm2_tc(tvb_handle* h, int epi, const Gemm2Maps& maps, const 
         case EPI_DUAL: return launch_gemm2_tc_t<EPI_DUAL>(h, maps, p, st, num_sms, cat);
         case EPI_F32: return launch_gemm2_tc_t<EPI_F32>(h, maps, p, st, num_sms, cat);
         case EPI_RESID_LN: return launch_gemm2_tc_t<EPI_RESID_LN>(h, maps, p, st, num_sms, cat);
+        case EPI_RESID_F32_ST: return launch_gemm2_tc_t<EPI_RESID_F32_ST>(h, maps, p, st, num_sms, cat);
+        case EPI_RESID_LN_ST: return launch_gemm2_tc_t<EPI_RESID_LN_ST>(h, maps, p, st, num_sms, cat);
+        case EPI_FOLD_GELU: return launch_gemm2_tc_t<EPI_FOLD_GELU>(h, maps, p, st, num_sms, cat);
     }
     return fail(TVB_ERR_INVALID, "unknown epilogue %d", epi);
 }
@@ -819,7 +841,7 @@ static int linear_ln(tvb_handle* h, const Lin& lin, const Act& a, const float* r
     return TVB_OK;
 }
 
-enum LinEpi { LE_PLAIN, LE_GELU, LE_RESID, LE_DUAL };
+enum LinEpi { LE_PLAIN, LE_GELU, LE_RESID, LE_DUAL, LE_RESID_ST /* + bf16 copy + row statistics */, LE_FOLD_GELU /* LN folded in */ };
 // LayerNorm whose fp32 result is not materialised: rows of `x` with per-row (mean, rstd) in `stats` and the norm's affine.
 struct LnRef {
     const float* x = nullptr;
@@ -842,11 +864,16 @@ static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, Li
         p.bias = lin.bias_tc; p.resid = ln ? ln->x : resid; p.out_f32 = out_f32; p.out_bf16 = out ? out->b16 : nullptr; p.ld_out = lin.N;
         if (ln) { p.ln_stats = ln->stats; p.ln_g = ln->g; p.ln_b = ln->b; }
         p.reverse = (rev && h->opt_zigzag) ? 1 : 0;
-        const int e = epi == LE_PLAIN ? EPI_BF16 : epi == LE_GELU ? EPI_GELU_BF16 : epi == LE_RESID ? (ln ? EPI_RESID_LN : EPI_RESID_F32) : EPI_DUAL;
+        const int e = epi == LE_PLAIN ? EPI_BF16 : epi == LE_GELU ? EPI_GELU_BF16 : epi == LE_RESID ? (ln ? EPI_RESID_LN : EPI_RESID_F32)
+                    : epi == LE_RESID_ST ? (ln ? EPI_RESID_LN_ST : EPI_RESID_F32_ST) : epi == LE_FOLD_GELU ? EPI_FOLD_GELU : EPI_DUAL;
+        if (epi == LE_RESID_ST) p.part = h->ln_part;
+        if (epi == LE_FOLD_GELU) { p.part = h->ln_part; p.stats_out = h->statsB; p.fold_c = lin.fold_c; }
+        if ((epi == LE_RESID_ST || epi == LE_FOLD_GELU) && !(h->opt_gemm_2cta && !h->opt_gemm_mc && lin.N % 256 == 0))
+            return fail(TVB_ERR_STATE, "internal: folded LayerNorm needs the CTA-pair GEMM");
         if (h->opt_gemm_2cta) {
             Gemm2Maps maps;
             maps.a = a.tm; maps.a2 = a2 ? a2->tm : a.tm; maps.b = lin.tm2;
-            if (epi == LE_PLAIN || epi == LE_GELU) maps.out = out->tm_out;
+            if (epi == LE_PLAIN || epi == LE_GELU || epi == LE_FOLD_GELU) maps.out = out->tm_out;
             else maps.out = f32_map(h, out_f32);
             maps.resid = f32_map(h, p.resid);
             if (h->opt_gemm_mc && Mp % 512 == 0) {
@@ -983,8 +1010,12 @@ static int run_estimator(tvb_handle* h, const float* y, const float* t_seq_dev, 
     const bool fuse = bf && h->opt_ln_fuse && !epi_ln;
     LnRef cur_ln;                      // LayerNorm that produced the current layer input (valid when fuse && !plain_resid)
     bool plain_resid = !fuse;          // the current layer input exists as fp32 rows in hres
+    // LN1 folded into the FFN-in GEMM (no LN1 kernel): needs the CTA-pair GEMM epilogues
+    const bool fold1 = fuse && h->opt_ln1_fold && h->opt_gemm_2cta && !h->opt_gemm_mc && c.intermediate_size % 256 == 0 && H == 1024;
+    // zigzag traversal: every kernel walks the row blocks opposite to the kernel that produced its main input (L2 reuse)
+    const bool ln0_rev = !fold1, skip_rev = fold1, f1_rev = !fold1, f2_rev = fold1, ln2_rev = !fold1;
     if (fuse) {
-        TRY(layernorm(h, h->xpre, nullptr, &h->slots[0], h->ln0_g, h->ln0_b, st, h->statsA, true));
+        TRY(layernorm(h, h->xpre, nullptr, &h->slots[0], h->ln0_g, h->ln0_b, st, h->statsA, ln0_rev));
         cur_ln.x = h->xpre; cur_ln.stats = h->statsA; cur_ln.g = h->ln0_g; cur_ln.b = h->ln0_b;
     } else {
         TRY(layernorm(h, h->xpre, h->hres, &h->slots[0], h->ln0_g, h->ln0_b, st));
@@ -998,11 +1029,11 @@ static int run_estimator(tvb_handle* h, const float* y, const float* t_seq_dev, 
             const Act* skip = &h->slots[--sp];
             // traversal directions (zigzag): LayerNorms that feed a layer run last-row-first, so the consumer of their output
             // (skip merge or QKV) runs first-row-first; a QKV fed by the skip merge runs last-row-first
-            TRY(linear(h, h->skip[l - nl / 2], *cur, skip, LE_DUAL, &h->hbB, nullptr, h->hres, st, PC_GEMM_SKIP, nullptr, false));
+            TRY(linear(h, h->skip[l - nl / 2], *cur, skip, LE_DUAL, &h->hbB, nullptr, h->hres, st, PC_GEMM_SKIP, nullptr, skip_rev));
             cur = &h->hbB;
             plain_resid = true;
         }
-        TRY(linear(h, lw.qkv, *cur, nullptr, LE_PLAIN, &h->qkv, nullptr, nullptr, st, PC_GEMM_QKV, nullptr, l >= nl / 2));
+        TRY(linear(h, lw.qkv, *cur, nullptr, LE_PLAIN, &h->qkv, nullptr, nullptr, st, PC_GEMM_QKV, nullptr, fold1 ? (l < nl / 2) : (l >= nl / 2)));
         TRY(attention(h, st));
         const bool last = (l == nl - 1);
         if (epi_ln) {
@@ -1015,15 +1046,22 @@ static int run_estimator(tvb_handle* h, const float* y, const float* t_seq_dev, 
         } else if (fuse) {
             // x1 = attn + (layer input) -> xalt ; LN1 -> hbB + statsB
             // attention wrote ctx first-row-first: O-proj walks back (rev), LN1 forward, FFN-in back, FFN-out forward, LN2 back
-            TRY(linear(h, lw.o, h->ctx, nullptr, LE_RESID, nullptr, h->hres, h->xalt, st, PC_GEMM_O, plain_resid ? nullptr : &cur_ln, true));
-            TRY(layernorm(h, h->xalt, nullptr, &h->hbB, lw.ln1_g, lw.ln1_b, st, h->statsB, false));
-            TRY(linear(h, lw.f1, h->hbB, nullptr, LE_GELU, &h->mid, nullptr, nullptr, st, PC_GEMM_F1, nullptr, true));
+            if (fold1) {
+                // x1 = attn + input -> xalt (fp32) and hbB (bf16, un-normalised) + partial row statistics; FFN-in consumes the raw
+                // rows with W1 diag(gamma1) and applies LN1 in its epilogue (it also leaves (mean, rstd) in statsB for FFN-out)
+                TRY(linear(h, lw.o, h->ctx, nullptr, LE_RESID_ST, &h->hbB, h->hres, h->xalt, st, PC_GEMM_O, plain_resid ? nullptr : &cur_ln, true));
+                TRY(linear(h, lw.f1_fold, h->hbB, nullptr, LE_FOLD_GELU, &h->mid, nullptr, nullptr, st, PC_GEMM_F1, nullptr, f1_rev));
+            } else {
+                TRY(linear(h, lw.o, h->ctx, nullptr, LE_RESID, nullptr, h->hres, h->xalt, st, PC_GEMM_O, plain_resid ? nullptr : &cur_ln, true));
+                TRY(layernorm(h, h->xalt, nullptr, &h->hbB, lw.ln1_g, lw.ln1_b, st, h->statsB, false));
+                TRY(linear(h, lw.f1, h->hbB, nullptr, LE_GELU, &h->mid, nullptr, nullptr, st, PC_GEMM_F1, nullptr, f1_rev));
+            }
             LnRef ln1;
             ln1.x = h->xalt; ln1.stats = h->statsB; ln1.g = lw.ln1_g; ln1.b = lw.ln1_b;
-            TRY(linear(h, lw.f2, h->mid, nullptr, LE_RESID, nullptr, nullptr, h->xpre, st, PC_GEMM_F2, &ln1, false));
+            TRY(linear(h, lw.f2, h->mid, nullptr, LE_RESID, nullptr, nullptr, h->xpre, st, PC_GEMM_F2, &ln1, f2_rev));
             Act* dst = (l < nl / 2 - 1) ? &h->slots[sp++] : &h->hbA;
             // the last layer's output feeds the fp32 output projection: materialise it
-            TRY(layernorm(h, h->xpre, last ? h->hres : nullptr, dst, lw.ln2_g, lw.ln2_b, st, h->statsA, true));
+            TRY(layernorm(h, h->xpre, last ? h->hres : nullptr, dst, lw.ln2_g, lw.ln2_b, st, h->statsA, ln2_rev));
             cur_ln.x = h->xpre; cur_ln.stats = h->statsA; cur_ln.g = lw.ln2_g; cur_ln.b = lw.ln2_b;
             plain_resid = false;
             cur = dst;
