@@ -250,7 +250,9 @@ constexpr int G2_EPI_WARPS = 8;
 constexpr int G2_EPI_TILE = 4096;                            // 32 rows x 128 B
 constexpr int G2_EPI_BUFS = 2;                               // staging tiles per epilogue warp (a third one measured no gain)
 constexpr int G2_SMEM_EPI = G2_STAGES * G2_STAGE_BYTES;
-constexpr int G2_SMEM_BAR = G2_SMEM_EPI + G2_EPI_WARPS * G2_EPI_BUFS * G2_EPI_TILE;
+constexpr int G2_EPI_TILE2 = 2048;                           // 32 rows x 64 B: bf16 copy of a 32 x 32 chunk (EPI_RESID_*_ST), 64-B swizzle
+constexpr int G2_SMEM_EPI2 = G2_SMEM_EPI + G2_EPI_WARPS * G2_EPI_BUFS * G2_EPI_TILE;
+constexpr int G2_SMEM_BAR = G2_SMEM_EPI2 + G2_EPI_WARPS * G2_EPI_BUFS * G2_EPI_TILE2;
 constexpr int G2_SMEM_BYTES = G2_SMEM_BAR + 1024 + 512;
 constexpr int G2_THREADS = 320;
 
@@ -258,6 +260,7 @@ struct Gemm2Maps {
     CUtensorMap a, a2, b;     // operands
     CUtensorMap out;          // fp32 [M,N] box 32x32 (EPI_RESID_F32 / EPI_DUAL / EPI_F32) or bf16 [M,N] box 64x32 (EPI_BF16 / EPI_GELU_BF16)
     CUtensorMap resid;        // fp32 [M,N] box 32x32 (EPI_RESID_F32)
+    CUtensorMap out2;         // bf16 [M,N] box 32x32, 64-B swizzle: un-normalised copy for the LayerNorm-folding consumer (EPI_RESID_*_ST)
 };
 
 // NP = CTA pairs per cluster.  NP == 1: the kernel described above.  NP == 2 (cluster of 4): the two pairs work on vertically
@@ -294,6 +297,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tm.a); tma_prefetch_desc(&tm.a2); tma_prefetch_desc(&tm.b); tma_prefetch_desc(&tm.out);
+        if (EPI == EPI_RESID_F32_ST || EPI == EPI_RESID_LN_ST) tma_prefetch_desc(&tm.out2);
         if (EPI == EPI_RESID_F32 || EPI == EPI_RESID_LN || EPI == EPI_RESID_F32_ST || EPI == EPI_RESID_LN_ST) tma_prefetch_desc(&tm.resid);
     }
     if (warp_idx == 1 && lane == 0) {
@@ -367,6 +371,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
         const int quad = warp_idx & 3;
         const int chalf = ew >> 2;                                // which 128 of the 256 accumulator columns
         uint8_t* stg = smem + G2_SMEM_EPI + ew * G2_EPI_BUFS * G2_EPI_TILE;
+        uint8_t* stg2 = smem + G2_SMEM_EPI2 + ew * G2_EPI_BUFS * G2_EPI_TILE2;
         uint64_t* rb = rbar + ew * G2_EPI_BUFS;
         const int r7 = lane & 7;
         uint32_t kc = 0;                                          // running chunk counter
@@ -483,11 +488,15 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                     if constexpr (kStats) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) { ps1 += v[j]; ps2 = fmaf(v[j], v[j], ps2); }
-                        uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(row + lane) * p.ld_out + col);
+                        // bf16 copy through its own staging tile (64-B rows, 16-B chunk j of row r at chunk j ^ ((r >> 1) & 3)) + TMA store:
+                        // per-row direct stores cost +30 % on this GEMM (profiles/r01)
+                        uint8_t* row2 = stg2 + buf * G2_EPI_TILE2 + lane * 64;
+                        const int x3 = (lane >> 1) & 3;
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                            *reinterpret_cast<uint4*>(row2 + ((j ^ x3) << 4)) =
+                                make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
                     }
                 } else if constexpr (kBf16Out) {
 #pragma unroll
@@ -511,6 +520,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                 __syncwarp();
                 if (lane == 0) {
                     tma_store_2d(&tm.out, tile_s, col, row);
+                    if constexpr (kStats) tma_store_2d(&tm.out2, stg2 + buf * G2_EPI_TILE2, col, row);
                     tma_store_commit();
                 }
                 if (++buf == G2_EPI_BUFS) { buf = 0; bpar ^= 1; }

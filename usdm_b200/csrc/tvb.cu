@@ -75,7 +75,7 @@ static int resolve_driver() {
 // 2-D row-major [rows, cols] (leading dimension ld elements), box = box_rows x box_cols (128 bytes wide), 128-byte swizzle.
 // Default element type bf16 (box 64 columns); f32 = true makes an fp32 map (box 32 columns).
 static int make_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols = 64,
-                     bool f32 = false) {
+                     bool f32 = false, bool sw64 = false) {
     TRY(resolve_driver());
     const int esz = f32 ? 4 : 2;
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
@@ -83,7 +83,7 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols
     cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(TVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
                                        (long long)rows, (long long)cols, (long long)ld);
@@ -115,6 +115,7 @@ struct Act {                 // an activation buffer [Mp, C] in the precision of
     int C = 0;
     CUtensorMap tm;          // A operand map (bf16 path): box 128 x 64
     CUtensorMap tm_out;      // epilogue TMA-store map (bf16 path): box 32 rows x 64 columns
+    CUtensorMap tm_out32;    // epilogue TMA-store map, box 32 rows x 32 columns, 64-B swizzle (hbB: bf16 copy written by EPI_RESID_*_ST)
 };
 struct LayerW {
     Lin qkv, o, f1, f2;
@@ -692,6 +693,7 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
         TRY(make_tmap(&h->mid.tm, h->mid.b16, Mp, F, F, 128));
         TRY(make_tmap(&h->qkv.tm_out, h->qkv.b16, Mp, 3 * H, 3 * H, 32));
         TRY(make_tmap(&h->mid.tm_out, h->mid.b16, Mp, F, F, 32));
+        TRY(make_tmap(&h->hbB.tm_out32, h->hbB.b16, Mp, H, H, 32, 32, false, true));
         TRY(make_tmap(&h->tm_xpre, h->xpre, Mp, H, H, 32, 32, true));
         TRY(make_tmap(&h->tm_hres, h->hres, Mp, H, H, 32, 32, true));
         TRY(make_tmap(&h->tm_xalt, h->xalt, Mp, H, H, 32, 32, true));
@@ -876,6 +878,7 @@ static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, Li
             if (epi == LE_PLAIN || epi == LE_GELU || epi == LE_FOLD_GELU) maps.out = out->tm_out;
             else maps.out = f32_map(h, out_f32);
             maps.resid = f32_map(h, p.resid);
+            if (epi == LE_RESID_ST) maps.out2 = out->tm_out32;
             if (h->opt_gemm_mc && Mp % 512 == 0) {
                 maps.b = lin.tm3;
                 return launch_gemm4_tc(h, e, maps, p, st, cat);
