@@ -152,7 +152,7 @@ int tvb_debug_attention(int device, const void* qkv_dev, void* ctx_dev, const in
                         int32_t nseq, int32_t rows, int32_t H, int32_t nheads, const float* slopes_dev, int32_t version,
                         int32_t poly, void* stream);
 
-/* Test hook: attention v4 launches write clock64() stamps of their first 16 CTAs into this device buffer (16 x 256 int64;
+/* Test hook: attention v4 launches write clock64() stamps of their first 16 CTAs into this device buffer (2 x 16 x 256 int64;
  * layout in attn4_tc.cuh); NULL (default) disables. */
 int tvb_debug_set_trace(void* trace_dev);
 

@@ -82,16 +82,17 @@ def bench_attn(out):
     def run(version, poly):
         engine.check(lib.tvb_debug_attention(0, P(qkv), P(ctx), s_arr, l_arr, len(lens), rows, H, NH, P(slopes), version, poly, ST()))
 
-    for tv in (4, 7):
+    for tv in (7,):
       # trace of v4 / v7 (the hook's own per-call overhead makes wall-clock timing of single launches meaningless here)
       for _ in range(3):
           run(tv, 0)
-      trace = torch.zeros(16 * 256, dtype=torch.int64, device="cuda")
+      trace = torch.zeros(2 * 16 * 256, dtype=torch.int64, device="cuda")
       engine.check(lib.tvb_debug_set_trace(P(trace)))
       run(tv, 0)
       torch.cuda.synchronize()
       engine.check(lib.tvb_debug_set_trace(None))
-      tr = trace.cpu().view(16, 256)
+      trf = trace.cpu()[16 * 256:].view(16, 256)
+      tr = trace.cpu()[:16 * 256].view(16, 256)
       for cta in (0, 5):
           row = tr[cta].tolist()
           t0 = row[0]
@@ -100,6 +101,10 @@ def bench_attn(out):
                    A_s_ready=[rel(row[16 + 2 * j]) for j in range(9)], A_p_done=[rel(row[17 + 2 * j]) for j in range(9)], A_end=rel(row[80]),
                    B_s_ready=[rel(row[96 + 2 * j]) for j in range(9)], B_p_done=[rel(row[97 + 2 * j]) for j in range(9)], B_end=rel(row[160]),
                    mma_p_recv=[rel(row[177 + n]) for n in range(18)])
+          if tv == 7:
+              fr = trf[cta].tolist()
+              d["A_fine"] = [[rel(fr[4 * j + k]) for k in range(4)] for j in range(9)]
+              d["B_fine"] = [[rel(fr[128 + 4 * j + k]) for k in range(4)] for j in range(9)]
           out.append(d)
           print(d, flush=True)
 

@@ -24,6 +24,7 @@ attn7_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
     // half A [16+2j] scores of block j visible / [17+2j] P of block j handed over, [80] output stored; half B the same at +80;
     // MMA thread [176] Q landed, [177+n] P of step n received.
     long long* tr = (trace != nullptr && blockIdx.x < 16) ? trace + blockIdx.x * 256 : nullptr;
+    long long* trf = tr ? trace + 16 * 256 + blockIdx.x * 256 : nullptr;   // fine stamps of the softmax row 0: [half * 128 + 4 j + k]
     if (tr && threadIdx.x == 128) tr[0] = clock64();
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A4_SMEM_BAR);
@@ -256,6 +257,7 @@ attn7_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                     } else {
                     tmem_ld_32x32(tmem_S, ca);
                     tmem_ld_wait_dep(ca);
+                    if (trf && r == 0 && j < 32) trf[half * 128 + 4 * j + 0] = clock64();     // first 32 score columns in registers
                     tmem_ld_32x32(tmem_S + 32, cb);
                     proc(ca, 0);
                     tmem_ld_wait_dep(cb);
@@ -267,6 +269,7 @@ attn7_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                     tmem_ld_wait_dep(cb);
                     proc(cb, 3);
                     }
+                    if (trf && r == 0 && j < 32) trf[half * 128 + 4 * j + 1] = clock64();     // exponentials / sums / bf16 packing done
                     float a0, a1;
                     unpack2f(acc2, a0, a1);
                     lsum = a0 + a1;
@@ -346,6 +349,7 @@ attn7_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                 // Every thread observes every phase of pv_done exactly once and BEFORE it lets PV(j) start (parity waits are only
                 // unambiguous within one phase).  PV(j-1) was issued a whole block ago, so this does not stall.
                 if (j > 0 && !pv_seen) mbar_wait(&pv_done[half], (j - 1) & 1);
+                if (trf && r == 0 && j < 32) trf[half * 128 + 4 * j + 2] = clock64();         // previous PV observed
                 l_run += lsum;
                 // ---- bf16 pairs of P into the first 64 columns of this S buffer (A operand of the PV MMA)
                 if (!(POLY >= 100 && (POLY & 4))) {                                   // (timing ablation 104: P never stored)
@@ -353,6 +357,7 @@ attn7_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                 for (int c = 0; c < 4; ++c) tmem_st_32x16(tmem_S + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&s[c * 16]));
                 tmem_st_wait();
                 } else { asm volatile("" :: "r"(s[0]), "r"(s[17]), "r"(s[34]), "r"(s[63])); }
+                if (trf && r == 0 && j < 32) trf[half * 128 + 4 * j + 3] = clock64();         // P stored to TMEM
                 tc_fence_before();
                 mbar_arrive(&p_ready[buf]);
                 if (tr && r == 0 && j < 32) tr[17 + half * 80 + 2 * j] = clock64();

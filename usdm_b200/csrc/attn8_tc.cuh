@@ -28,8 +28,9 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
     uint64_t* kv_empty = kv_full + A4_KV_STAGES;        // [4]
     uint64_t* s_full = kv_empty + A4_KV_STAGES;         // [3] per S buffer
     uint64_t* p_ready = s_full + 3;                     // [3] per S buffer
-    uint64_t* pv_done = p_ready + 3;                    // [2] per half
-    uint64_t* o_free = pv_done + 2;                     // [2] per half: O has been read out by the 128 softmax threads
+    uint64_t* pv_done = p_ready + 3;                    // [2 halves][2]: PV number c of a half arrives on [half][c & 1] (phase c >> 1), so a
+                                                        //   thread may wait for PV(c) without having observed every earlier phase (see below)
+    uint64_t* o_free = pv_done + 4;                     // [2] per half: O has been read out by the 128 softmax threads
     uint64_t* s_free = o_free + 2;                      // [3] per S buffer: the PV MMA that read P from it has retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 3);
 
@@ -41,7 +42,7 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
     if (warp_idx == 1 && lane == 0) {
         for (int s = 0; s < 2; ++s) {
             mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); mbar_init(&ext_full[s], 1); mbar_init(&ext_empty[s], 1);
-            mbar_init(&pv_done[s], 1); mbar_init(&o_free[s], 128);
+            mbar_init(&pv_done[2 * s], 1); mbar_init(&pv_done[2 * s + 1], 1); mbar_init(&o_free[s], 128);
         }
         for (int s = 0; s < A4_KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
         for (int s = 0; s < 3; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_ready[s], 128); mbar_init(&s_free[s], 1); }
@@ -118,6 +119,7 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
         constexpr uint32_t idesc_pv = make_idesc_bf16(128, ATT_D, false, true);          // B (= V) MN-major
         const uint64_t dv0 = make_smem_desc_sw128(smem_u32(smem + A6_SMEM_KV + ATT_TILE_BYTES), 8192, 1024);
         int buf = 0, slot = 0, cntA = 0, cntB = 0;          // cntX: items in which half X has taken part so far
+        int pvA = 0, pvB = 0;                               // PV MMAs issued so far per half
         uint32_t bpar = 0;
         A6Item w = a6_load_item(work, blockIdx.x, nheads);
         for (int t = blockIdx.x; t < n_items; t += G) {
@@ -135,11 +137,13 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                     const uint32_t tP = tmem_base + buf * 128;
                     const uint32_t tO = tmem_base + 384 + half * 64;
                     const uint64_t dv = dv0 + static_cast<uint64_t>(slot * (2 * ATT_TILE_BYTES >> 4));
+                    const int pvc = half ? pvB : pvA;
+                    if (half) ++pvB; else ++pvA;
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < ATT_BK / 16; ++k)                             // V rows [16k, 16k+16); P: 8 columns per K step
                             umma_ts(tO, tP + k * 8, dv + k * (2048 >> 4), idesc_pv, (j | k) != 0);
-                        umma_commit(&pv_done[half]);
+                        umma_commit(&pv_done[2 * half + (pvc & 1)]);
                         umma_commit(&s_free[buf]);
                         if (half == w.nh - 1) umma_commit(&kv_empty[slot]);               // every MMA reading this stage has been issued
                     }
@@ -220,6 +224,16 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
             const int i = qt + r;                           // query position in the sequence
             const float a0d = -slope2 * static_cast<float>(r);   // diagonal block: -sigma |r - e| = min(A, -A), A = sigma e - sigma r
             float m_ref = 0.f, l_run = 0.f;
+            // PV(c) of this half retired?  Two alternating barriers per half make this wait unambiguous without observing every
+            // phase: the scores of the current block exist, hence (s_free chain, in-order PV issue) PV(c - 2) of this half has
+            // retired, hence barrier [c & 1] is in the phase of PV(c) or past it.
+            auto wait_pv = [&](int c) { mbar_wait(&pv_done[2 * half + (c & 1)], (c >> 1) & 1); };
+            // s[0,64): bf16 pairs of P (output); fast path: s[64,96) / s[96,128) double-buffer 32-column chunks of S.  The first chunk
+            // of block j + 1 is requested before P of block j is stored (the scores are there already), so its latency and the
+            // barrier round trip overlap the store / hand-over of block j.
+            uint32_t s[128];
+            uint32_t(&ca)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
+            uint32_t(&cb)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
             for (int j = 0; j < nkb; ++j) {
                 const int ng = gbase + (w.two ? 2 * j + half : j);
                     const int k0 = j * ATT_BK;
@@ -229,12 +243,10 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                     const bool partial = (k0 + ATT_BK > len);
                     // additive term of this block: per-row constant (off-diagonal; the j-dependent part came out of the MMA) or none
                     const float c_row = diag ? 0.f : -slope2 * fabsf(static_cast<float>(i - k0));
-                    mbar_wait(&s_full[buf], (ng / 3) & 1);
-                    tc_fence_after();
-                    // s[0,64): bf16 pairs of P (output); fast path: s[64,96) / s[96,128) double-buffer 32-column chunks of S
-                    uint32_t s[128];
-                    uint32_t(&ca)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
-                    uint32_t(&cb)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
+                    if (j == 0) {                            // later blocks: waited for and first chunk requested at the end of block j - 1
+                        mbar_wait(&s_full[buf], (ng / 3) & 1);
+                        tc_fence_after();
+                    }
                     float lsum = 0.f;
                     bool need_full = (j == 0);
                     if (j > 0) {
@@ -284,8 +296,7 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                                 s[c * 16 + u] = pack_bf16x2(lo, hi);
                             }
                         };
-                        tmem_ld_32x32(tmem_S, ca);
-                        tmem_ld_wait_dep(ca);
+                        tmem_ld_wait_dep(ca);                // chunk 0 was requested at the end of the previous block
                         tmem_ld_32x32(tmem_S + 32, cb);
                         proc(ca, 0);
                         tmem_ld_wait_dep(cb);
@@ -341,7 +352,7 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                             const float alpha = ex2_approx(m_ref - m_new);    // 1 for rows whose reference stays
                             m_ref = m_new;
                             l_run *= alpha;
-                            mbar_wait(&pv_done[half], (pvbase + j - 1) & 1);          // O is only stable once the previous PV has retired
+                            wait_pv(pvbase + j - 1);                                  // O is only stable once the previous PV has retired
                             pv_seen = true;
                             tc_fence_after();
 #pragma unroll
@@ -372,10 +383,13 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                         unpack2f(acc2, a0, a1);
                         lsum = a0 + a1;
                     }
-                    // Every thread observes every phase of pv_done exactly once and BEFORE it lets PV(j) start (parity waits are only
-                    // unambiguous within one phase).  PV(j-1) was issued a whole block ago, so this does not stall.
-                    if (j > 0 && !pv_seen) mbar_wait(&pv_done[half], (pvbase + j - 1) & 1);
                     l_run += lsum;
+                    if (j + 1 < nkb) {                       // scores of the next block: wait, then request their first 32 columns
+                        const int ng1 = ng + w.nh;
+                        mbar_wait(&s_full[ng1 % 3], (ng1 / 3) & 1);
+                        tc_fence_after();
+                        tmem_ld_32x32(tmem_base + (ng1 % 3) * 128 + lane_off, ca);
+                    }
                     // ---- bf16 pairs of P into the first 64 columns of this S buffer (A operand of the PV MMA)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) tmem_st_32x16(tmem_S + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&s[c * 16]));
@@ -389,7 +403,8 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
             // phase): they wait on a named barrier that the half-A threads reach after observing the item's last scores.
             if (!w.two) asm volatile("bar.arrive 1, 256;" ::: "memory");
             // epilogue: read O, hand the accumulator back, then O / l -> ctx (bf16), only rows that belong to the sequence
-            mbar_wait(&pv_done[half], (pvbase + nkb - 1) & 1);
+            if (nkb >= 2) wait_pv(pvbase + nkb - 2);       // (one-half items: makes the next wait unambiguous, see wait_pv)
+            wait_pv(pvbase + nkb - 1);
             tc_fence_after();
             uint32_t o[64];
 #pragma unroll
