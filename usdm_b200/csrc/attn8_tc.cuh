@@ -14,7 +14,20 @@
 
 namespace tvb {
 
-template <int POLY>
+// Two MUFU.EX2 whose issue is tied (through an always-true predicate the compiler cannot prove) to `pace`, a value produced by the
+// tail of an EARLIER element pair.  Without it ptxas emits the 32 MUFUs of a chunk back to back (8 issue cycles each on this warp)
+// and only then the adds / converts; with it the program order alternates MUFU pairs with the tails of the pairs before, so the FMA
+// and ALU pipes work inside the MUFU issue gaps (measured pipe costs: tools/pipe_bench.cu).
+__device__ __forceinline__ void ex2_pair_paced(float& lo, float& hi, float pace) {
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.ge.f32 p, %2, 0f00000000;\n\t"
+        "@p ex2.approx.ftz.f32 %0, %0;\n\t"
+        "@p ex2.approx.ftz.f32 %1, %1;\n\t}\n"
+        : "+f"(lo), "+f"(hi)
+        : "f"(pace));
+}
+
+template <int POLY, bool PACE>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ ctx, int H, int nheads,
              const float* __restrict__ slopes, const int4* __restrict__ work, int n_items) {
@@ -255,7 +268,8 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                         // maximum is only checked afterwards.
                         const float off = c_row - m_ref;
                         const uint64_t off2 = pack2f(off, off);
-                        uint64_t acc2 = pack2f(0.f, 0.f);
+                        uint64_t acc2 = pack2f(0.f, 0.f), accp2 = pack2f(0.f, 0.f);
+                        float pace_a = 0.f, pace_b = 0.f;
                         float mxa = -INFINITY, mxb = -INFINITY;
                         auto proc = [&](uint32_t(&cur)[32], const int c) {
                             if (diag) {
@@ -285,12 +299,25 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                                 uint64_t p2;
                                 if (POLY > 0 && (u % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) {
                                     p2 = exp2_poly2(x2);
+                                    accp2 = fadd2(accp2, p2);               // polynomial pairs: own accumulator, off the pacing chain
                                 } else {
                                     float lo, hi;
                                     unpack2f(x2, lo, hi);
-                                    p2 = pack2f(ex2_approx(lo), ex2_approx(hi));
+                                    if constexpr (PACE) {
+                                        ex2_pair_paced(lo, hi, pace_a);
+                                    } else {
+                                        lo = ex2_approx(lo);
+                                        hi = ex2_approx(hi);
+                                    }
+                                    p2 = pack2f(lo, hi);
+                                    acc2 = fadd2(acc2, p2);
+                                    if constexpr (PACE) {
+                                        float al, ah;
+                                        unpack2f(acc2, al, ah);
+                                        pace_a = pace_b;                    // the MUFU pair after the next one waits for this sum
+                                        pace_b = al;
+                                    }
                                 }
-                                acc2 = fadd2(acc2, p2);
                                 float lo, hi;
                                 unpack2f(p2, lo, hi);
                                 s[c * 16 + u] = pack_bf16x2(lo, hi);
@@ -308,7 +335,7 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                         tmem_ld_wait_dep(cb);
                         proc(cb, 3);
                         float a0, a1;
-                        unpack2f(acc2, a0, a1);
+                        unpack2f(fadd2(acc2, accp2), a0, a1);
                         lsum = a0 + a1;
                         const float m_blk = fmaxf(mxa, mxb) + c_row;          // block maximum in the true (biased) domain
                         // P must stay <= 2^16: if any row of the warp outgrew its reference, redo the block the careful way
@@ -438,28 +465,35 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
     }
 }
 
-template <int POLY>
+template <int POLY, bool PACE>
 inline cudaError_t launch_attn8_t(const CUtensorMap& tmQKV, __nv_bfloat16* ctx, int H, int nheads, const float* slopes, const int4* work,
                                   int nwork, int num_sms, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(attn8_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(attn8_kernel<POLY, PACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr = true;
     }
     const int n_items = nwork * nheads;
     const int grid = n_items < num_sms ? n_items : num_sms;
-    attn8_kernel<POLY><<<grid, ATT_THREADS, A6_SMEM_BYTES, st>>>(tmQKV, ctx, H, nheads, slopes, work, n_items);
+    attn8_kernel<POLY, PACE><<<grid, ATT_THREADS, A6_SMEM_BYTES, st>>>(tmQKV, ctx, H, nheads, slopes, work, n_items);
     return cudaGetLastError();
 }
 // The q columns of tmQKV must have been produced with W_q, b_q scaled by head_dim^-0.5 * log2(e).
 inline cudaError_t launch_attn8_raw(const CUtensorMap& tmQKV, __nv_bfloat16* ctx, int H, int nheads, const float* slopes,
-                                    const int4* work, int nwork, int poly, int num_sms, cudaStream_t st) {
+                                    const int4* work, int nwork, int poly, int num_sms, cudaStream_t st, bool pace = true) {
+    if (pace) switch (poly) {
+        case 0: return launch_attn8_t<0, true>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
+        case 2: return launch_attn8_t<2, true>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
+        case 3: return launch_attn8_t<3, true>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
+        case 4: return launch_attn8_t<4, true>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
+        default: return cudaErrorInvalidValue;
+    }
     switch (poly) {
-        case 0: return launch_attn8_t<0>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
-        case 2: return launch_attn8_t<2>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
-        case 3: return launch_attn8_t<3>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
-        case 4: return launch_attn8_t<4>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
+        case 0: return launch_attn8_t<0, false>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
+        case 2: return launch_attn8_t<2, false>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
+        case 3: return launch_attn8_t<3, false>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
+        case 4: return launch_attn8_t<4, false>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
         default: return cudaErrorInvalidValue;
     }
 }

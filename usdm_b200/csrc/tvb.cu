@@ -143,6 +143,7 @@ struct tvb_handle {
                                 // measured 7 % slower with multicast, profiles/r01: the pair kernel is not L2->SM bound after all)
     int opt_attn_ptmem = 1;     // tcgen05 attention v3: 1 = P kept in tensor memory (TS MMA), 0 = P staged through shared memory
     int opt_attn_v = 8;         // tcgen05 attention kernel generation: 8 = attn8_tc.cuh (default), 7 .. 4 = attnN_tc.cuh, 3 = attn_tc.cuh
+    int opt_attn_pace = 1;      // attention v8: 1 = MUFU pairs paced by an earlier pair's tail (forces ptxas to interleave pipes), 0 = free order
     int opt_attn_poly = 3;      // attention v4+: 0 = every exp2 on MUFU, n = one element pair in n on the FMA-pipe polynomial (default 3)
     int opt_ln_fuse = 1;        // bf16 path: 2 = LayerNorm fused into the residual GEMM epilogue (8-CTA clusters, gemmln_tc.cuh);
                                 //            1 = LayerNorm writes bf16 + (mean, rstd) only and the residual GEMM epilogue re-normalises
@@ -545,6 +546,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     else if (!strcmp(name, "attn_ptmem")) h->opt_attn_ptmem = value ? 1 : 0;
     else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 8) return fail(TVB_ERR_INVALID, "attn_v must be 3 .. 8"); h->opt_attn_v = value; }
     else if (!strcmp(name, "attn_poly")) { if (value != 0 && value != 2 && value != 3 && value != 4 && !(value >= 100 && value < 108)) return fail(TVB_ERR_INVALID, "attn_poly must be 0, 2, 3 or 4"); h->opt_attn_poly = value; }
+    else if (!strcmp(name, "attn_pace")) h->opt_attn_pace = value ? 1 : 0;
     else if (!strcmp(name, "ln_fuse")) { if (value < 0 || value > 2) return fail(TVB_ERR_INVALID, "ln_fuse must be 0, 1 or 2"); h->opt_ln_fuse = value; }
     else if (!strcmp(name, "profile")) { h->profile = value ? 1 : 0; h->ev_used = 0; h->ev_cat.clear(); }
     else return fail(TVB_ERR_INVALID, "unknown option %s", name);
@@ -920,7 +922,7 @@ static int attention(tvb_handle* h, cudaStream_t st) {
     ProfScope ps(h, st, PC_ATTN);
     // bf16 path: q carries head_dim^-0.5 * log2(e) (tvb_finalize_weights), so tensor-core scores are already in the log2 domain
     if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 8) {
-        CK(launch_attn8_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_poly, h->num_sms, st));
+        CK(launch_attn8_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_poly, h->num_sms, st, h->opt_attn_pace != 0));
     } else if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 7) {
         CK(launch_attn7_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_poly, st));
     } else if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 6) {
