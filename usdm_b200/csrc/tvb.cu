@@ -143,7 +143,8 @@ struct tvb_handle {
                                 // measured 7 % slower with multicast, profiles/r01: the pair kernel is not L2->SM bound after all)
     int opt_attn_ptmem = 1;     // tcgen05 attention v3: 1 = P kept in tensor memory (TS MMA), 0 = P staged through shared memory
     int opt_attn_v = 8;         // tcgen05 attention kernel generation: 8 = attn8_tc.cuh (default), 7 .. 4 = attnN_tc.cuh, 3 = attn_tc.cuh
-    int opt_attn_pace = 1;      // attention v8: 1 = MUFU pairs paced by an earlier pair's tail (forces ptxas to interleave pipes), 0 = free order
+    int opt_attn_pace = 0;      // attention v8: 1 = MUFU pairs paced by an earlier pair's tail (forces ptxas to interleave the pipes in program
+                                // order; measured 2-15 % SLOWER: the added dependency latency outweighs it), 0 = free order (default)
     int opt_attn_poly = 3;      // attention v4+: 0 = every exp2 on MUFU, n = one element pair in n on the FMA-pipe polynomial (default 3)
     int opt_ln_fuse = 1;        // bf16 path: 2 = LayerNorm fused into the residual GEMM epilogue (8-CTA clusters, gemmln_tc.cuh);
                                 //            1 = LayerNorm writes bf16 + (mean, rstd) only and the residual GEMM epilogue re-normalises
@@ -880,7 +881,7 @@ static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, Li
             if (epi == LE_PLAIN || epi == LE_GELU || epi == LE_FOLD_GELU) maps.out = out->tm_out;
             else maps.out = f32_map(h, out_f32);
             maps.resid = f32_map(h, p.resid);
-            if (epi == LE_RESID_ST) maps.out2 = out->tm_out32;
+            if (epi == LE_RESID_ST || epi == LE_DUAL) maps.out2 = out->tm_out32;
             if (h->opt_gemm_mc && Mp % 512 == 0) {
                 maps.b = lin.tm3;
                 return launch_gemm4_tc(h, e, maps, p, st, cat);
@@ -1215,6 +1216,7 @@ extern "C" int tvb_debug_gemm_bf16(int device, const void* a_dev, const void* w_
         else TRY(make_tmap(&maps.out, out_f32_dev, M, N, N, 32, 32, true));
         if (e == EPI_RESID_F32) TRY(make_tmap(&maps.resid, resid_dev, M, N, N, 32, 32, true));
         else maps.resid = maps.out;
+        if (e == EPI_DUAL) TRY(make_tmap(&maps.out2, out_bf16_dev, M, N, N, 32, 32, false, true));
         if (mc) return launch_gemm4_tc(nullptr, e, maps, p, static_cast<cudaStream_t>(stream));
         return launch_gemm2_tc(nullptr, e, maps, p, static_cast<cudaStream_t>(stream), prop.multiProcessorCount);
     }
