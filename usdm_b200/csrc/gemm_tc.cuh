@@ -297,7 +297,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tm.a); tma_prefetch_desc(&tm.a2); tma_prefetch_desc(&tm.b); tma_prefetch_desc(&tm.out);
-        if (EPI == EPI_RESID_F32_ST || EPI == EPI_RESID_LN_ST || EPI == EPI_DUAL) tma_prefetch_desc(&tm.out2);
+        if (EPI == EPI_RESID_F32_ST || EPI == EPI_RESID_LN_ST) tma_prefetch_desc(&tm.out2);
         if (EPI == EPI_RESID_F32 || EPI == EPI_RESID_LN || EPI == EPI_RESID_F32_ST || EPI == EPI_RESID_LN_ST) tma_prefetch_desc(&tm.resid);
     }
     if (warp_idx == 1 && lane == 0) {
@@ -508,21 +508,20 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<float4*>(rowp + ((j ^ r7) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    if constexpr (EPI == EPI_DUAL) {               // bf16 copy for the next GEMM: own staging tile + TMA store (as *_ST)
-                        uint8_t* row2 = stg2 + buf * G2_EPI_TILE2 + lane * 64;
-                        const int x3 = (lane >> 1) & 3;
+                    if constexpr (EPI == EPI_DUAL) {               // bf16 copy for the next GEMM (12 launches / pass, K = 2048): direct stores
+                        // (staging it like *_ST measured 8 % slower here: the longer mainloop hides the per-row stores)
+                        uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(row + lane) * p.ld_out + col);
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<uint4*>(row2 + ((j ^ x3) << 4)) =
-                                make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                            o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
                     }
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
                     tma_store_2d(&tm.out, tile_s, col, row);
-                    if constexpr (kStats || EPI == EPI_DUAL) tma_store_2d(&tm.out2, stg2 + buf * G2_EPI_TILE2, col, row);
+                    if constexpr (kStats) tma_store_2d(&tm.out2, stg2 + buf * G2_EPI_TILE2, col, row);
                     tma_store_commit();
                 }
                 if (++buf == G2_EPI_BUFS) { buf = 0; bpar ^= 1; }
