@@ -63,7 +63,8 @@ def generate_sharded(generate_fn: Callable, x: torch.Tensor, cond: torch.Tensor,
     for mb in micro_batches(mine, lens, max_tokens):
         idx = torch.tensor(mb, dtype=torch.long, device=cond.device)
         tmax = max(max(lens[i] for i in mb), 1)
-        out = generate_fn(x[idx][:, :tmax].contiguous(), cond[idx][:, :, :tmax].contiguous(), lengths[idx], **gen_kwargs)
+        lens_mb = torch.tensor([lens[i] for i in mb], dtype=torch.int64)          # host tensor: lengths may live on either device
+        out = generate_fn(x[idx][:, :tmax].contiguous(), cond[idx][:, :, :tmax].contiguous(), lens_mb, **gen_kwargs)
         local[pos:pos + len(mb), :, :tmax] = out
         pos += len(mb)
     if world == 1:
