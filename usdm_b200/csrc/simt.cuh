@@ -459,6 +459,9 @@ __global__ void k_fold_rows(const float* __restrict__ W, const __nv_bfloat16* __
     for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
     if (lane == 0) { c_out[row] = c; b_out[row] = bias[row] + b; }
 }
+__global__ void k_fill_f32(float* __restrict__ out, int n, float v) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = v;
+}
 __global__ void k_f32_to_bf16(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
         out[i] = __float2bfloat16_rn(in[i]);

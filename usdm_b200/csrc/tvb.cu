@@ -138,6 +138,8 @@ struct tvb_handle {
     int opt_gemm_2cta = 1;      // bf16 path: 1 = CTA-pair (cta_group::2) GEMM, 0 = single-CTA GEMM
     int opt_ln1_fold = 1;       // bf16 path with ln_fuse == 1: LN1 folded into the FFN-in GEMM (no LN1 kernel, attention-out epilogue emits
                                 // a bf16 copy + row statistics); 0 = LN1 as a kernel
+    int opt_graph = 1;          // 1 = small batches (<= 16384 packed rows) replay one estimator pass as a CUDA graph inside tvb_solve
+                                // (the pass is ~230 launches; at B = 1 the host cannot feed them fast enough), 0 = always launch directly
     int opt_zigzag = 1;         // bf16 path: row-block traversal alternates between producer and consumer kernels (L2 reuse)
     int opt_gemm_mc = 0;        // CTA-pair GEMM: 1 = clusters of two pairs sharing the W tile by TMA multicast, 0 = independent pairs (default:
                                 // measured 7 % slower with multicast, profiles/r01: the pair kernel is not L2->SM bound after all)
@@ -178,6 +180,14 @@ struct tvb_handle {
     int2* d_work16 = nullptr; int work16_cap = 0, n_work16 = 0;        // 16-query tiles (CUDA-core attention)
     int4* d_work128 = nullptr; int work128_cap = 0, n_work128 = 0;     // ATT_BQ-query tiles (tcgen05 attention)
     float* d_tseq = nullptr;
+    // CUDA graphs of one estimator pass, keyed by the state pointer they read (tvb_solve: z_work, z_hat); dropped whenever the
+    // plan, the precision or an option changes (graph_epoch)
+    struct PassGraph { const float* y = nullptr; cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+    PassGraph graphs[2];
+    cudaStream_t cap_stream = nullptr;                  // capture happens on a private stream (the caller's may be the legacy default
+                                                        // stream, which cannot be captured); the graph is launched on the caller's
+    std::vector<int64_t> plan_lengths;
+    int plan_precision = -1;
     int plan_B = 0, plan_T = 0, plan_cfg = 0, plan_half = 0;
     float* base = nullptr;
     Act hin, p1, slots[32], hbA, hbB, qkv, ctx, mid;
@@ -187,6 +197,8 @@ struct tvb_handle {
     float *z_work = nullptr, *z_hat = nullptr, *v_pred = nullptr;
     CUtensorMap tm_xpre, tm_xalt, tm_hres;       // fp32 [Mp, H] epilogue maps (box 32 rows x 32 columns): TMA store / residual load
 };
+
+static void drop_graphs(tvb_handle* h);
 
 // per-kernel timing scopes (only active when option "profile" is set)
 enum ProfCat { PC_GEMM = 0, PC_ATTN = 1, PC_CONV = 2, PC_NORM = 3, PC_FRAME = 4, PC_OUT = 5,
@@ -282,6 +294,8 @@ extern "C" int tvb_destroy(tvb_handle* h) {
     for (void* p : h->owned) cudaFree(p);
     for (void* p : h->ws_owned) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    drop_graphs(h);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     delete h;
     return TVB_OK;
 }
@@ -531,6 +545,7 @@ extern "C" int tvb_set_precision(tvb_handle* h, int32_t precision) {
     if (!h) return fail(TVB_ERR_INVALID, "null handle");
     if (precision != TVB_PRECISION_BF16 && precision != TVB_PRECISION_FP32_VALIDATE) return fail(TVB_ERR_INVALID, "unknown precision %d", precision);
     h->precision = precision;
+    drop_graphs(h);
     return TVB_OK;
 }
 extern "C" int tvb_get_precision(const tvb_handle* h) { return h ? h->precision : TVB_ERR_INVALID; }
@@ -538,11 +553,13 @@ extern "C" int64_t tvb_kernel_launches(const tvb_handle* h) { return h ? h->laun
 extern "C" int64_t tvb_device_bytes(const tvb_handle* h) { return h ? static_cast<int64_t>(h->dev_bytes + h->ws_bytes) : 0; }
 extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     if (!h || !name) return fail(TVB_ERR_INVALID, "null argument");
+    drop_graphs(h);
     if (!strcmp(name, "attn_tc")) h->opt_attn_tc = value ? 1 : 0;
     else if (!strcmp(name, "conv_tc")) h->opt_conv_tc = value ? 1 : 0;
     else if (!strcmp(name, "gemm_2cta")) h->opt_gemm_2cta = value ? 1 : 0;
     else if (!strcmp(name, "gemm_mc")) h->opt_gemm_mc = value ? 1 : 0;
     else if (!strcmp(name, "zigzag")) h->opt_zigzag = value ? 1 : 0;
+    else if (!strcmp(name, "graph")) h->opt_graph = value ? 1 : 0;
     else if (!strcmp(name, "ln1_fold")) h->opt_ln1_fold = value ? 1 : 0;
     else if (!strcmp(name, "attn_ptmem")) h->opt_attn_ptmem = value ? 1 : 0;
     else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 8) return fail(TVB_ERR_INVALID, "attn_v must be 3 .. 8"); h->opt_attn_v = value; }
@@ -576,7 +593,19 @@ static int alloc_f32(tvb_handle* h, float** p, size_t n) {
     return TVB_OK;
 }
 
+static void drop_graphs(tvb_handle* h) {
+    for (auto& g : h->graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        g = tvb_handle::PassGraph();
+    }
+}
+
 static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int cfg_double, cudaStream_t st) {
+    // same batch layout as the previous call (the usual serving loop): keep the plan, the workspace and the captured graphs
+    if (h->finalized && B == h->plan_B && T == h->plan_T && cfg_double == h->plan_cfg && h->plan_precision == h->precision &&
+        static_cast<int>(h->plan_lengths.size()) == B && std::equal(h->plan_lengths.begin(), h->plan_lengths.end(), lengths))
+        return TVB_OK;
+    drop_graphs(h);
     const tvb_config& c = h->cfg;
     if (!h->finalized) return fail(TVB_ERR_STATE, "tvb_finalize_weights has not been called");
     if (B <= 0 || T <= 0) return fail(TVB_ERR_INVALID, "B and T must be positive");
@@ -685,6 +714,8 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
     h->L.seq_utt = h->d_seq + 2 * nseq;
     h->L.seq_uncond = h->d_seq + 3 * nseq;
     h->plan_B = B; h->plan_T = T; h->plan_cfg = cfg_double; h->plan_half = half;
+    h->plan_lengths.assign(lengths, lengths + B);
+    h->plan_precision = h->precision;
     if (bf) {   // A-operand maps cover exactly the Mp live rows: TMA zero-fills anything outside
         TRY(make_tmap(&h->hin.tm, h->hin.b16, Mp, H, H, 128));
         TRY(make_tmap(&h->p1.tm, h->p1.b16, Mp, H, H, 128));
@@ -1090,6 +1121,46 @@ static int run_estimator(tvb_handle* h, const float* y, const float* t_seq_dev, 
     return TVB_OK;
 }
 
+// One estimator pass at uniform time t inside the ODE loop.  Small batches are launch-bound (a pass is ~230 kernels of a few
+// microseconds each): the pass is captured once per state pointer into a CUDA graph that reads t from device memory and is
+// replayed afterwards; large batches launch directly.
+static int run_estimator_step(tvb_handle* h, const float* y, float t, cudaStream_t st) {
+    const bool use_graph = h->opt_graph && !h->profile && h->L.Mp <= 16384;
+    if (!use_graph) return run_estimator(h, y, nullptr, t, st);
+    k_fill_f32<<<1, 128, 0, st>>>(h->d_tseq, h->L.nseq, t);
+    h->launches++;
+    CKL();
+    tvb_handle::PassGraph* g = nullptr;
+    for (auto& c : h->graphs)
+        if (c.y == y) g = &c;                              // captured, or reserved by the first (direct) pass with this pointer
+    if (!g) {
+        for (auto& c : h->graphs)
+            if (c.y == nullptr) { g = &c; break; }
+        if (!g) { drop_graphs(h); g = &h->graphs[0]; }
+        // first pass with this state pointer: run it directly (one-time attribute set-up happens here), capture the second
+        g->y = y;
+        return run_estimator(h, y, h->d_tseq, 0.f, st);
+    }
+    if (!g->exec) {
+        const int64_t l0 = h->launches;
+        cudaGraph_t graph = nullptr;
+        if (!h->cap_stream) CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+        CK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = run_estimator(h, y, h->d_tseq, 0.f, h->cap_stream);
+        const cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
+        if (rc != TVB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return fail(TVB_ERR_CUDA, "graph capture of the estimator pass failed: %s", cudaGetErrorString(ce));
+        g->launches = h->launches - l0;
+        h->launches = l0;
+        const cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { g->exec = nullptr; return fail(TVB_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+    }
+    CK(cudaGraphLaunch(g->exec, st));
+    h->launches += g->launches;
+    return TVB_OK;
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // public compute entry points
 // ----------------------------------------------------------------------------------------------------------------
@@ -1162,7 +1233,7 @@ extern "C" int tvb_solve(tvb_handle* h, int32_t solver, const int64_t* x_dev, co
     volatile float dt = t_span_host[1] - t_span_host[0];
     int noise_i = 0, eval_i = 0;
     for (int step = 1; step <= n_steps; ++step) {
-        TRY(run_estimator(h, h->z_work, nullptr, t, st));
+        TRY(run_estimator_step(h, h->z_work, t, st));
         const float t_next = t + dt;
         const bool corrector = (solver == TVB_SOLVER_HEUN) && (step < n_steps);
         p.dt = dt; p.t_next = t_next;
@@ -1176,7 +1247,7 @@ extern "C" int tvb_solve(tvb_handle* h, int32_t solver, const int64_t* x_dev, co
         ++eval_i;
         t = t_next;
         if (corrector) {
-            TRY(run_estimator(h, h->z_hat, nullptr, t, st));
+            TRY(run_estimator_step(h, h->z_hat, t, st));
             p.z_base = h->z_work; p.v_prev = h->v_pred;
             p.eps = P > 0 ? prompt_noise_dev + static_cast<size_t>(noise_i++) * n : nullptr;
             p.z_out = h->z_work;
