@@ -78,7 +78,8 @@ int tvb_get_precision(const tvb_handle* h);
  * kernel emits bf16 + row statistics and the residual GEMM epilogue re-normalises the fp32 stream; 0 = separate fp32 LayerNorm output), "ln1_fold" (with ln_fuse = 1: 1 = the LayerNorm between attention and FFN is folded into the FFN-in GEMM, default;
  * 0 = it runs as a kernel), "zigzag" (1 = producer / consumer kernels walk the rows in opposite directions for L2 reuse,
  * default), "graph" (1 = tvb_solve replays the estimator pass of small batches as a CUDA graph, default; 0 = direct launches),
- * "attn_pace" (attention v8 MUFU pacing ablation, default 0), and "profile" (see tvb_profile_read). */
+ * "pdl" (1 = GEMM / attention / LayerNorm kernels use programmatic dependent launch, default), "attn_pace" (attention v8 MUFU
+ * pacing ablation, default 0), and "profile" (see tvb_profile_read). */
 int tvb_set_option(tvb_handle* h, const char* name, int32_t value);
 
 /* Replaces: Transformer.forward(x, y, cond, t, lengths) (networks.py:302-374) — the per-step velocity estimator.

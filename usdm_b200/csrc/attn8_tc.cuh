@@ -62,10 +62,12 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
         fence_barrier_init();
     }
     if (warp_idx == 2) tmem_alloc<512>(tmem_slot);
+    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                      // set-up above overlapped the tail of the QKV GEMM
 
     if (warp_idx < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -467,7 +469,7 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
 
 template <int POLY, bool PACE>
 inline cudaError_t launch_attn8_t(const CUtensorMap& tmQKV, __nv_bfloat16* ctx, int H, int nheads, const float* slopes, const int4* work,
-                                  int nwork, int num_sms, cudaStream_t st) {
+                                  int nwork, int num_sms, cudaStream_t st, bool pdl) {
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(attn8_kernel<POLY, PACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6_SMEM_BYTES);
@@ -476,24 +478,29 @@ inline cudaError_t launch_attn8_t(const CUtensorMap& tmQKV, __nv_bfloat16* ctx, 
     }
     const int n_items = nwork * nheads;
     const int grid = n_items < num_sms ? n_items : num_sms;
-    attn8_kernel<POLY, PACE><<<grid, ATT_THREADS, A6_SMEM_BYTES, st>>>(tmQKV, ctx, H, nheads, slopes, work, n_items);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(ATT_THREADS); cfg.dynamicSmemBytes = A6_SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, attn8_kernel<POLY, PACE>, tmQKV, ctx, H, nheads, slopes, work, n_items);
 }
 // The q columns of tmQKV must have been produced with W_q, b_q scaled by head_dim^-0.5 * log2(e).
 inline cudaError_t launch_attn8_raw(const CUtensorMap& tmQKV, __nv_bfloat16* ctx, int H, int nheads, const float* slopes,
-                                    const int4* work, int nwork, int poly, int num_sms, cudaStream_t st, bool pace = true) {
+                                    const int4* work, int nwork, int poly, int num_sms, cudaStream_t st, bool pace = true, bool pdl = false) {
     if (pace) switch (poly) {
-        case 0: return launch_attn8_t<0, true>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
-        case 2: return launch_attn8_t<2, true>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
-        case 3: return launch_attn8_t<3, true>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
-        case 4: return launch_attn8_t<4, true>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
+        case 0: return launch_attn8_t<0, true>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st, pdl);
+        case 2: return launch_attn8_t<2, true>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st, pdl);
+        case 3: return launch_attn8_t<3, true>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st, pdl);
+        case 4: return launch_attn8_t<4, true>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st, pdl);
         default: return cudaErrorInvalidValue;
     }
     switch (poly) {
-        case 0: return launch_attn8_t<0, false>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
-        case 2: return launch_attn8_t<2, false>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
-        case 3: return launch_attn8_t<3, false>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
-        case 4: return launch_attn8_t<4, false>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st);
+        case 0: return launch_attn8_t<0, false>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st, pdl);
+        case 2: return launch_attn8_t<2, false>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st, pdl);
+        case 3: return launch_attn8_t<3, false>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st, pdl);
+        case 4: return launch_attn8_t<4, false>(tmQKV, ctx, H, nheads, slopes, work, nwork, num_sms, st, pdl);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -32,6 +32,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 // ------------------------------------------------------------------------------------------
+// programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start (and run its
+// set-up: barrier init, TMEM allocation, descriptor prefetch) while the previous kernel of the stream drains; pdl_wait() blocks
+// until that kernel has completed and flushed.  pdl_launch_dependents() lets the NEXT kernel do the same with this one.
+// Both are no-ops for kernels launched the ordinary way.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

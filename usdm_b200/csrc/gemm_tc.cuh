@@ -307,10 +307,12 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
         fence_barrier_init();
     }
     if (warp_idx == 2) tmem_alloc_2cta<512>(tmem_slot);
+    pdl_launch_dependents();
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                      // everything above overlapped the tail of the previous kernel
 
     if (warp_idx == 0) {
         if (elect_one()) {      // one elected lane: the compiler then keeps descriptors / addresses in uniform registers

@@ -122,6 +122,8 @@ k_layernorm(const float* __restrict__ x, float* __restrict__ y, TB* __restrict__
             int reverse) {
     // y == nullptr (with stats != nullptr): the fp32 result is not materialised; consumers that need it (the residual add of
     // the next GEMM epilogue, EPI_RESID_LN) recompute it from x and the (mean, rstd) written to stats[row].
+    pdl_launch_dependents();
+    pdl_wait();
     const int row_fwd = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row_fwd >= Mp) return;

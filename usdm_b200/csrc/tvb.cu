@@ -138,6 +138,8 @@ struct tvb_handle {
     int opt_gemm_2cta = 1;      // bf16 path: 1 = CTA-pair (cta_group::2) GEMM, 0 = single-CTA GEMM
     int opt_ln1_fold = 1;       // bf16 path with ln_fuse == 1: LN1 folded into the FFN-in GEMM (no LN1 kernel, attention-out epilogue emits
                                 // a bf16 copy + row statistics); 0 = LN1 as a kernel
+    int opt_pdl = 1;            // 1 = GEMM / attention / LayerNorm kernels are launched with programmatic stream serialization: their set-up
+                                // overlaps the tail of the previous kernel (griddepcontrol), 0 = ordinary launches
     int opt_graph = 1;          // 1 = small batches (<= 16384 packed rows) replay one estimator pass as a CUDA graph inside tvb_solve
                                 // (the pass is ~230 launches; at B = 1 the host cannot feed them fast enough), 0 = always launch directly
     int opt_zigzag = 1;         // bf16 path: row-block traversal alternates between producer and consumer kernels (L2 reuse)
@@ -560,6 +562,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     else if (!strcmp(name, "gemm_mc")) h->opt_gemm_mc = value ? 1 : 0;
     else if (!strcmp(name, "zigzag")) h->opt_zigzag = value ? 1 : 0;
     else if (!strcmp(name, "graph")) h->opt_graph = value ? 1 : 0;
+    else if (!strcmp(name, "pdl")) h->opt_pdl = value ? 1 : 0;
     else if (!strcmp(name, "ln1_fold")) h->opt_ln1_fold = value ? 1 : 0;
     else if (!strcmp(name, "attn_ptmem")) h->opt_attn_ptmem = value ? 1 : 0;
     else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 8) return fail(TVB_ERR_INVALID, "attn_v must be 3 .. 8"); h->opt_attn_v = value; }
@@ -778,9 +781,14 @@ static int launch_gemm2_tc_t(tvb_handle* h, const Gemm2Maps& maps, const GemmPar
     const int tiles = (p.M / 256) * (p.N / 256);
     int grid = 2 * tiles < (num_sms & ~1) ? 2 * tiles : (num_sms & ~1);
     ProfScope ps(h, st, cat);
-    gemm2_tc_kernel<EPI><<<grid, G2_THREADS, G2_SMEM_BYTES, st>>>(maps, p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(G2_THREADS); cfg.dynamicSmemBytes = G2_SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (h && h->opt_pdl) ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, gemm2_tc_kernel<EPI>, maps, p));
     if (h) h->launches++;
-    CKL();
     return TVB_OK;
 }
 template <int EPI>
@@ -941,7 +949,17 @@ static int layernorm(tvb_handle* h, const float* x, float* y, Act* yb, const flo
     const int Mp = h->L.Mp, H = h->cfg.hidden_size;
     ProfScope ps(h, st, PC_NORM);
     if (h->precision == TVB_PRECISION_BF16)
-        k_layernorm<bf16><<<(Mp + 7) / 8, 256, 0, st>>>(x, y, yb ? yb->b16 : nullptr, g, b, h->L.row_seq, Mp, H, 1e-5f, stats, (rev && h->opt_zigzag) ? 1 : 0);
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((Mp + 7) / 8); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = h->opt_pdl ? 1 : 0;
+        bf16* ybp = yb ? yb->b16 : nullptr;
+        const int* rs = h->L.row_seq;
+        CK(cudaLaunchKernelEx(&cfg, k_layernorm<bf16>, x, y, ybp, g, b, rs, Mp, H, 1e-5f, stats, (rev && h->opt_zigzag) ? 1 : 0));
+    }
     else
         k_layernorm<float><<<(Mp + 7) / 8, 256, 0, st>>>(x, y, yb ? yb->f32 : nullptr, g, b, h->L.row_seq, Mp, H, 1e-5f, stats, 0);
     h->launches++;
@@ -954,7 +972,7 @@ static int attention(tvb_handle* h, cudaStream_t st) {
     ProfScope ps(h, st, PC_ATTN);
     // bf16 path: q carries head_dim^-0.5 * log2(e) (tvb_finalize_weights), so tensor-core scores are already in the log2 domain
     if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 8) {
-        CK(launch_attn8_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_poly, h->num_sms, st, h->opt_attn_pace != 0));
+        CK(launch_attn8_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_poly, h->num_sms, st, h->opt_attn_pace != 0, h->opt_pdl != 0));
     } else if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 7) {
         CK(launch_attn7_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_poly, st));
     } else if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 6) {
