@@ -243,6 +243,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // to its row in place, and one elected lane TMA-stores the tile: all global traffic is coalesced by the TMA engine.
 // ================================================================================================================
 constexpr int G2_STAGES = 4;
+#ifndef G2_EXTRA_STAGE
+#define G2_EXTRA_STAGE 1      // epilogues without the bf16 copy staging run a 5-deep operand ring (see gemm_pair_body)
+#endif
 constexpr int G2_A_BYTES = 128 * GEMM_BK * 2;                // 16 KB (this CTA's 128 rows of A)
 constexpr int G2_B_BYTES = 128 * GEMM_BK * 2;                // 16 KB (this CTA's half of the 256 W rows)
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
@@ -274,9 +277,16 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
     extern __shared__ uint8_t smem_raw[];
     // identical carve-up in both CTAs (the dynamic smem base offset is the same for every CTA of a kernel)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_SMEM_BAR);
-    uint64_t* empty_bar = full_bar + G2_STAGES;
-    uint64_t* tfull_bar = empty_bar + G2_STAGES;
+    // operand ring depth: the *_ST epilogues need the extra bf16 staging tiles (32 KB), everything else spends that memory on a
+    // fifth stage (an operand tile comes back ~1-2 k cycles after its TMA is issued when the L2 is busy; 4 stages = 2 k cycles of MMA)
+    constexpr int kStages = (EPI == EPI_RESID_F32_ST || EPI == EPI_RESID_LN_ST) ? G2_STAGES : G2_STAGES + G2_EXTRA_STAGE;
+    constexpr int kSmemEpi = kStages * G2_STAGE_BYTES;
+    constexpr int kSmemEpi2 = kSmemEpi + G2_EPI_WARPS * G2_EPI_BUFS * G2_EPI_TILE;
+    constexpr int kSmemBar = (kStages == G2_STAGES) ? kSmemEpi2 + G2_EPI_WARPS * G2_EPI_BUFS * G2_EPI_TILE2 : kSmemEpi2;
+    static_assert(kSmemBar + 1024 + 512 <= G2_SMEM_BYTES, "shared memory budget");
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSmemBar);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tfull_bar = empty_bar + kStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint64_t* rbar = tempty_bar + 2;                  // [8 warps][G2_EPI_BUFS] residual-tile arrival
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + G2_EPI_BUFS * G2_EPI_WARPS);
@@ -301,7 +311,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
         if (EPI == EPI_RESID_F32 || EPI == EPI_RESID_LN || EPI == EPI_RESID_F32_ST || EPI == EPI_RESID_LN_ST) tma_prefetch_desc(&tm.resid);
     }
     if (warp_idx == 1 && lane == 0) {
-        for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NP); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NP); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * G2_EPI_WARPS); }
         for (int s = 0; s < G2_EPI_BUFS * G2_EPI_WARPS; ++s) mbar_init(&rbar[s], 1);
         fence_barrier_init();
@@ -333,7 +343,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                                             static_cast<uint16_t>(0x5u << cta));
                     } else
                     tma_load_2d_2cta(sa + G2_A_BYTES, &tm.b, &full_bar[stage], k0, n0);
-                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -355,7 +365,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k) umma_ss_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                     umma_commit_2cta(&empty_bar[stage], NP == 2 ? 0xF : 0x3);   // every CTA that writes into these stages
-                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit_2cta(&tfull_bar[as], static_cast<uint16_t>(0x3u << (2 * pair_id)));
             }
@@ -372,8 +382,8 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
         const int ew = warp_idx - 2;
         const int quad = warp_idx & 3;
         const int chalf = ew >> 2;                                // which 128 of the 256 accumulator columns
-        uint8_t* stg = smem + G2_SMEM_EPI + ew * G2_EPI_BUFS * G2_EPI_TILE;
-        uint8_t* stg2 = smem + G2_SMEM_EPI2 + ew * G2_EPI_BUFS * G2_EPI_TILE2;
+        uint8_t* stg = smem + kSmemEpi + ew * G2_EPI_BUFS * G2_EPI_TILE;
+        uint8_t* stg2 = smem + kSmemEpi2 + ew * G2_EPI_BUFS * G2_EPI_TILE2;   // only used (and only inside the budget) by the *_ST epilogues
         uint64_t* rb = rbar + ew * G2_EPI_BUFS;
         const int r7 = lane & 7;
         uint32_t kc = 0;                                          // running chunk counter
