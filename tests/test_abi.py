@@ -1,4 +1,4 @@
-"""CPU: the C-ABI library loads, exports every symbol include/tvb.h declares, and fails loudly without a GPU."""
+"""CPU: the C-ABI library loads, exports every symbol include/*.h declares, and fails loudly without a GPU."""
 import ctypes as C
 import os
 import re
@@ -10,9 +10,12 @@ from util import CFG, ROOT
 
 
 def _declared_symbols():
-    txt = open(os.path.join(ROOT, "include", "tvb.h")).read()
-    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(tvb_[a-z0-9_]+)\s*\(", txt)))
+    import glob
+    syms = set()
+    for path in sorted(glob.glob(os.path.join(ROOT, "include", "*.h"))):
+        txt = re.sub(r"/\*.*?\*/", "", open(path).read(), flags=re.S)
+        syms |= set(re.findall(r"\b(tvb_[a-z0-9_]+)\s*\(", txt))
+    return sorted(syms)
 
 
 def test_library_exports_every_declared_symbol():

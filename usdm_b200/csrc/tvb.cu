@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/tvb.h"
+#include "../../include/tvb_vocoder.h"
 #include "attn_tc.cuh"
 #include "attn4_tc.cuh"
 #include "attn5_tc.cuh"
@@ -27,6 +28,7 @@
 #include "gemmln_tc.cuh"
 #include "glue.cuh"
 #include "simt.cuh"
+#include "vocoder.cuh"
 
 using namespace tvb;
 typedef __nv_bfloat16 bf16;
@@ -1396,3 +1398,8 @@ extern "C" int tvb_mel_spectrogram(int device, const float* wav_dev, int64_t n_s
     CKL();
     return TVB_OK;
 }
+
+// ----------------------------------------------------------------------------------------------------------------
+// BigVGAN vocoder path (include/tvb_vocoder.h)
+// ----------------------------------------------------------------------------------------------------------------
+#include "vocoder_host.inl"

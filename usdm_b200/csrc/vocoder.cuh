@@ -1,0 +1,426 @@
+// BigVGAN v1 vocoder kernels (reference src/decoder/voicebox/vocoder/models.py:192-222).
+//
+// Activations are TIME-MAJOR: x[b][t][c] (c contiguous), so a 1-D convolution over time is a GEMM whose A operand is the
+// activation matrix shifted by (tap - taps/2) * dilation ROWS per tap -- the shift is a TMA coordinate and the zero padding at
+// both ends of every utterance is TMA's out-of-bounds fill on the time axis of a 3-D (channel, time, batch) tensor map, so no
+// im2col buffer exists.  A ConvTranspose1d(k = 2u, stride u, pad u/2) (models.py:158-163) is the same kernel: 3 taps and
+// N = u * C_out outputs per input step, row [u * C_out] of step t being output steps t*u .. t*u+u-1 (weights regrouped once).
+//   voc_conv_tc_kernel : tcgen05 implicit-GEMM conv; warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue, persistent,
+//                        smem operand ring + 2 TMEM accumulators; epilogue out = alpha * (acc + bias + resid) (+ out).
+//   k_voc_act          : Activation1d (alias_free_torch/act.py:21-27): x2 kaiser-sinc upsample (polyphase, replicate edges),
+//                        Snake / SnakeBeta (activations.py:40-50, :107-119), x2 low-pass downsample -- one pass, registers only.
+//   k_voc_conv_f32     : CUDA-core fp32 conv with the same epilogue (validation path, <= 1e-5 of the reference).
+//   k_voc_post         : conv_post (C -> 1, k = 7) + tanh (models.py:217-219).
+#pragma once
+#include "common.cuh"
+
+namespace tvb {
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// weight preparation (run once)
+// ------------------------------------------------------------------------------------------------------------------------------
+// weight_norm (dim 0): w[i][...] = g[i] * v[i][...] / ||v[i]||   (torch.nn.utils.weight_norm, models.py:32-50,149,160,185)
+__global__ void k_voc_weight_norm(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ w, int inner) {
+    __shared__ float red[32];
+    const float* vi = v + static_cast<size_t>(blockIdx.x) * inner;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < inner; i += blockDim.x) s += vi[i] * vi[i];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) red[0] = s;
+    }
+    __syncthreads();
+    const float sc = g[blockIdx.x] / sqrtf(red[0]);
+    float* wi = w + static_cast<size_t>(blockIdx.x) * inner;
+    for (int i = threadIdx.x; i < inner; i += blockDim.x) wi[i] = vi[i] * sc;
+}
+
+// Conv1d weight [co][ci][k]  ->  tensor-core operand W2[n][tap][ci_pad] (bf16, zero padded) and CUDA-core operand Wt[tap][ci][n].
+__global__ void k_voc_pack_conv(const float* __restrict__ w, int Cout, int Cin, int k, int n_pad, int ci_pad, __nv_bfloat16* __restrict__ w2,
+                                float* __restrict__ wt) {
+    const size_t total = static_cast<size_t>(n_pad) * k * ci_pad;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int ci = static_cast<int>(i % ci_pad), tap = static_cast<int>((i / ci_pad) % k), n = static_cast<int>(i / (static_cast<size_t>(ci_pad) * k));
+        float v = 0.f;
+        if (n < Cout && ci < Cin) {
+            v = w[(static_cast<size_t>(n) * Cin + ci) * k + tap];
+            wt[(static_cast<size_t>(tap) * Cin + ci) * Cout + n] = v;
+        }
+        w2[i] = __float2bfloat16(v);
+    }
+}
+// ConvTranspose1d weight [ci][co][k], stride u, padding (k - u) / 2  ->  3-tap conv with N = u * Cout:
+//   out[t*u + r][co] = sum_s sum_ci x[t + s - 1][ci] * W[ci][co][r + pad + (1 - s) * u]     (taps outside [0, k) are zero)
+__global__ void k_voc_pack_convT(const float* __restrict__ w, int Cin, int Cout, int k, int u, int n_pad, int ci_pad,
+                                 __nv_bfloat16* __restrict__ w2, float* __restrict__ wt) {
+    const int N = u * Cout, pad = (k - u) / 2;
+    const size_t total = static_cast<size_t>(n_pad) * 3 * ci_pad;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int ci = static_cast<int>(i % ci_pad), s = static_cast<int>((i / ci_pad) % 3), n = static_cast<int>(i / (static_cast<size_t>(ci_pad) * 3));
+        float v = 0.f;
+        if (n < N && ci < Cin) {
+            const int r = n / Cout, co = n % Cout, j = r + pad + (1 - s) * u;
+            if (j >= 0 && j < k) v = w[(static_cast<size_t>(ci) * Cout + co) * k + j];
+            wt[(static_cast<size_t>(s) * Cin + ci) * N + n] = v;
+        }
+        w2[i] = __float2bfloat16(v);
+    }
+}
+__global__ void k_voc_tile_bias(const float* __restrict__ b, int Cout, int N, float* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) out[i] = b[i % Cout];
+}
+// per-channel snake constants: (alpha', 1 / (beta' + 1e-9)) with alpha' = exp(alpha) when log-scale (activations.py:112-117)
+__global__ void k_voc_snake_consts(const float* __restrict__ alpha, const float* __restrict__ beta, int C, int logscale, float2* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float a = alpha[c], b = beta[c];
+    if (logscale) { a = expf(a); b = expf(b); }
+    out[c] = make_float2(a, 1.0f / (b + 1e-9f));
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// layout changes
+// ------------------------------------------------------------------------------------------------------------------------------
+// mel [B][C][T] fp32 (reference layout, models.py:192)  ->  time-major [B][T][ld] in OutT
+template <typename OutT>
+__global__ void k_voc_mel_in(const float* __restrict__ mel, int C, int T, int ld, OutT* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const float* src = mel + static_cast<size_t>(b) * C * T;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, t = t0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && t < T) ? src[static_cast<size_t>(c) * T + t] : 0.f;
+    }
+    __syncthreads();
+    OutT* dst = out + static_cast<size_t>(b) * T * ld;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int t = t0 + i, c = c0 + threadIdx.x;
+        if (t < T && c < C) dst[static_cast<size_t>(t) * ld + c] = static_cast<OutT>(tile[threadIdx.x][i]);
+    }
+}
+// time-major [B][T][C] -> [B][C][T] (test hook output)
+__global__ void k_voc_tm_to_cm(const float* __restrict__ x, int C, int T, float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const float* src = x + static_cast<size_t>(b) * T * C;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int t = t0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && t < T) ? src[static_cast<size_t>(t) * C + c] : 0.f;
+    }
+    __syncthreads();
+    float* dst = out + static_cast<size_t>(b) * C * T;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, t = t0 + threadIdx.x;
+        if (t < T && c < C) dst[static_cast<size_t>(c) * T + t] = tile[threadIdx.x][i];
+    }
+}
+// fp32 [rows][C] -> bf16 [rows][ld]   (operand copy of a stage output for the next upsampling conv)
+__global__ void k_voc_to_bf16(const float* __restrict__ x, size_t rows, int C, int ld, __nv_bfloat16* __restrict__ out) {
+    const size_t total = rows * C;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t r = i / C;
+        const int c = static_cast<int>(i - r * C);
+        out[r * ld + c] = __float2bfloat16(x[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// Activation1d: up x2 (12-tap kaiser-sinc, replicate edges, gain 2) -> snake -> low-pass + down x2 (12 taps, replicate edges)
+//   u[2q]   = 2 * sum_m f[2m+1] * x[clamp(q + 2 - m)]         u[2q+1] = 2 * sum_m f[2m] * x[clamp(q + 3 - m)]       m = 0..5
+//   v       = u + inv_b * sin^2(a * u)
+//   y[t]    = sum_j f[j] * v[clamp(2t + j - 5, 0, 2T-1)]                                                            j = 0..11
+// (resample.py:22-30 and filter.py:86-94 written out per output phase; checked against the reference form in the CPU test-suite.)
+// One thread = one channel x VOC_ACT_TT consecutive outputs; x, (v_even, v_odd) windows live in registers.
+// ------------------------------------------------------------------------------------------------------------------------------
+constexpr int VOC_ACT_TT = 64;
+struct VocFilt { float up[12]; float dn[12]; };
+
+template <typename OutT>
+__global__ void __launch_bounds__(128)
+k_voc_act(const float* __restrict__ x, int C, int T, int ld_out, const float2* __restrict__ consts, VocFilt F, OutT* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;              // block = (channels, time chunks): 32..128 x 4..1
+    const int b = blockIdx.z, t0 = (blockIdx.y * blockDim.y + threadIdx.y) * VOC_ACT_TT;
+    if (c >= C || t0 >= T) return;
+    const float* xb = x + static_cast<size_t>(b) * T * C + c;
+    OutT* ob = out + static_cast<size_t>(b) * T * ld_out + c;
+    const float2 ab = consts[c];
+    auto ldx = [&](int t) { t = t < 0 ? 0 : (t >= T ? T - 1 : t); return __ldg(xb + static_cast<size_t>(t) * C); };
+    // x window xw[i] = x[q - 3 + i], i = 0..6, for the current q
+    float xw[7];
+    int q = t0 - 3;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xw[i + 1] = ldx(q - 3 + i);       // shifted in below
+    float ve[7], vo[7];                                            // (v[2q'], v[2q'+1]) for q' = q-6 .. q
+#pragma unroll
+    for (int i = 0; i < 7; ++i) ve[i] = vo[i] = 0.f;
+    const int t_end = min(t0 + VOC_ACT_TT, T);
+    for (; q <= t_end + 2; ++q) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) xw[i] = xw[i + 1];
+        xw[6] = ldx(q + 3);
+        // replicate padding of v: positions left of 0 take v[0], right of 2T-1 take v[2T-1]; evaluate at the clamped q
+        float e, o;
+        if (q >= 0 && q < T) {
+            float ue = 0.f, uo = 0.f;
+#pragma unroll
+            for (int m = 0; m < 6; ++m) {
+                ue = fmaf(F.up[2 * m + 1], xw[5 - m], ue);         // x[q + 2 - m] = xw[5 - m]
+                uo = fmaf(F.up[2 * m], xw[6 - m], uo);             // x[q + 3 - m] = xw[6 - m]
+            }
+            ue *= 2.f; uo *= 2.f;
+            const float se = sinf(ue * ab.x), so = sinf(uo * ab.x);
+            e = fmaf(ab.y, se * se, ue);
+            o = fmaf(ab.y, so * so, uo);
+        } else {
+            // outside the signal: recompute the edge sample (q = 0 even phase, or q = T-1 odd phase) from the clamped window
+            const int qc = q < 0 ? 0 : T - 1;
+            float uu = 0.f;
+#pragma unroll
+            for (int m = 0; m < 6; ++m) uu = fmaf(q < 0 ? F.up[2 * m + 1] : F.up[2 * m], ldx(qc + (q < 0 ? 2 : 3) - m), uu);
+            uu *= 2.f;
+            const float s = sinf(uu * ab.x);
+            e = o = fmaf(ab.y, s * s, uu);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { ve[i] = ve[i + 1]; vo[i] = vo[i + 1]; }
+        ve[6] = e; vo[6] = o;
+        const int t = q - 3;                                       // window now holds q' = t-3 .. t+3
+        if (t >= t0 && t < t_end) {
+            float y = F.dn[0] * vo[0];
+#pragma unroll
+            for (int d = 1; d <= 5; ++d) {
+                y = fmaf(F.dn[2 * d - 1], ve[d], y);
+                y = fmaf(F.dn[2 * d], vo[d], y);
+            }
+            y = fmaf(F.dn[11], ve[6], y);
+            ob[static_cast<size_t>(t) * ld_out] = static_cast<OutT>(y);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// conv epilogue shared by both conv kernels:  out = alpha * (acc + bias[n] + resid) (+ out when accumulate)
+// ------------------------------------------------------------------------------------------------------------------------------
+struct VocConvParams {
+    int B, T, Cin, N;            // T = input (= output) time steps per utterance, N = outputs per step (u * C_out for the upsamplers)
+    int taps, dil;               // tap s reads input step t + (s - taps/2) * dil
+    int ci_pad, n_pad, bn;       // padded K per tap (multiple of 64), padded N (multiple of bn), N tile
+    const float* bias;           // [N]
+    const float* resid;          // [B][T][N] or nullptr
+    float* out;                  // [B][T][N]
+    float alpha;
+    int accumulate;
+};
+
+// CUDA-core fp32 reference conv (validation path): thread = (4 consecutive time steps, n); Wt[tap][ci][n] coalesced over n.
+__global__ void __launch_bounds__(128)
+k_voc_conv_f32(const float* __restrict__ x, const float* __restrict__ wt, VocConvParams p) {
+    const int n = blockIdx.y * blockDim.x + threadIdx.x;
+    const int t0 = blockIdx.x * 4, b = blockIdx.z;
+    if (n >= p.N) return;
+    const float* xb = x + static_cast<size_t>(b) * p.T * p.Cin;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < p.taps; ++s) {
+        const int sh = (s - p.taps / 2) * p.dil;
+        const float* w = wt + static_cast<size_t>(s) * p.Cin * p.N + n;
+        const float* xr[4];
+        bool ok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int t = t0 + i + sh;
+            ok[i] = t >= 0 && t < p.T && t0 + i < p.T;
+            xr[i] = xb + static_cast<size_t>(ok[i] ? t : 0) * p.Cin;
+        }
+        for (int ci = 0; ci < p.Cin; ++ci) {
+            const float wv = __ldg(w + static_cast<size_t>(ci) * p.N);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = fmaf(ok[i] ? __ldg(xr[i] + ci) : 0.f, wv, acc[i]);
+        }
+    }
+    const float bv = p.bias[n];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int t = t0 + i;
+        if (t >= p.T) break;
+        const size_t off = (static_cast<size_t>(b) * p.T + t) * p.N + n;
+        float v = acc[i] + bv;
+        if (p.resid) v += p.resid[off];
+        v *= p.alpha;
+        if (p.accumulate) v += p.out[off];
+        p.out[off] = v;
+    }
+}
+
+// tcgen05 implicit-GEMM conv.  A: 3-D map (Cin, T, B) bf16, box 64 x 128 x 1, 128-byte swizzle.  W: 2-D map [n_pad][taps * ci_pad],
+// box 64 x bn.  K loop = taps x (ci_pad / 64) stages; tile = (128 time steps, bn outputs) of one utterance.
+constexpr int VC_BM = 128;
+constexpr int VC_A_BYTES = VC_BM * 64 * 2;
+constexpr int VC_THREADS = 192;
+template <int ACC_COLS> struct VcCfg {
+    static constexpr int kStages = ACC_COLS > 64 ? 4 : 6;
+    static constexpr int kBBytes = ACC_COLS * 64 * 2;
+    static constexpr int kStageBytes = VC_A_BYTES + kBBytes;
+    static constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
+};
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+template <int ACC_COLS>        // TMEM columns per accumulator (>= bn): 256 or 64
+__global__ void __launch_bounds__(VC_THREADS, 1)
+voc_conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, VocConvParams p) {
+    using Cfg = VcCfg<ACC_COLS>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + Cfg::kStages;
+    uint64_t* tfull_bar = empty_bar + Cfg::kStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (p.T + VC_BM - 1) / VC_BM, n_tiles = p.n_pad / p.bn;
+    const int num_tiles = p.B * m_tiles * n_tiles;
+    const int kc = p.ci_pad / 64, ksteps = p.taps * kc;
+    const uint32_t stage_tx = VC_A_BYTES + static_cast<uint32_t>(p.bn) * 128u;
+
+    if (warp_idx == 0 && lane == 0) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW); }
+    if (warp_idx == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp_idx == 2) tmem_alloc<2 * ACC_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp_idx == 0) {
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % n_tiles, mt = (tile / n_tiles) % m_tiles, b = tile / (n_tiles * m_tiles);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const int tap = ks / kc, k0 = (ks - tap * kc) * 64;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::kStageBytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+                    tma_load_3d(sa, &tmX, &full_bar[stage], k0, mt * VC_BM + (tap - p.taps / 2) * p.dil, b);
+                    tma_load_2d(sa + VC_A_BYTES, &tmW, &full_bar[stage], tap * p.ci_pad + k0, nt * p.bn);
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(128, p.bn);
+            int stage = 0; uint32_t phase = 0; int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * ACC_COLS;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+                    const uint64_t db = make_smem_desc_sw128(sa + VC_A_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[as]);
+            }
+        }
+    } else {
+        const int quad = warp_idx & 3;
+        const bool vec = (p.N & 3) == 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const int nt = tile % n_tiles, mt = (tile / n_tiles) % m_tiles, b = tile / (n_tiles * m_tiles);
+            mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+            tc_fence_after();
+            const int t = mt * VC_BM + quad * 32 + lane;
+            const bool row_ok = t < p.T;
+            const size_t row_off = (static_cast<size_t>(b) * p.T + (row_ok ? t : 0)) * p.N;
+#pragma unroll 1
+            for (int c = 0; c < p.bn / 16; ++c) {
+                uint32_t r[16];
+                tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * ACC_COLS + c * 16, r);
+                tmem_ld_wait();
+                const int n0 = nt * p.bn + c * 16;
+                if (!row_ok || n0 >= p.N) continue;
+                if (vec) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int n = n0 + 4 * j;
+                        if (n >= p.N) break;
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                        float4 v = make_float4(__uint_as_float(r[4 * j]) + bv.x, __uint_as_float(r[4 * j + 1]) + bv.y,
+                                               __uint_as_float(r[4 * j + 2]) + bv.z, __uint_as_float(r[4 * j + 3]) + bv.w);
+                        if (p.resid) {
+                            const float4 q = *reinterpret_cast<const float4*>(p.resid + row_off + n);
+                            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+                        }
+                        v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
+                        float4* o = reinterpret_cast<float4*>(p.out + row_off + n);
+                        if (p.accumulate) { const float4 q = *o; v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+                        *o = v;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = n0 + j;
+                        if (n < p.N) {
+                            float v = __uint_as_float(r[j]) + p.bias[n];
+                            if (p.resid) v += p.resid[row_off + n];
+                            v *= p.alpha;
+                            if (p.accumulate) v += p.out[row_off + n];
+                            p.out[row_off + n] = v;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 2) {
+        tc_fence_after();
+        tmem_dealloc<2 * ACC_COLS>(tmem_base);
+    }
+}
+
+// conv_post (C -> 1, k = 7, pad 3) + tanh (models.py:217-219); x is the fp32 output of activation_post, time-major [B][T][C].
+__global__ void k_voc_post(const float* __restrict__ x, int C, int T, const float* __restrict__ w /* [C][7] */, const float* __restrict__ bias,
+                           float* __restrict__ wav /* [B][T] */) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (t >= T) return;
+    const float* xb = x + static_cast<size_t>(b) * T * C;
+    float acc = bias[0];
+    for (int j = 0; j < 7; ++j) {
+        const int tt = t + j - 3;
+        if (tt < 0 || tt >= T) continue;
+        const float* xr = xb + static_cast<size_t>(tt) * C;
+        for (int c = 0; c < C; ++c) acc = fmaf(xr[c], __ldg(w + c * 7 + j), acc);
+    }
+    wav[static_cast<size_t>(b) * T + t] = tanhf(acc);
+}
+
+}  // namespace tvb

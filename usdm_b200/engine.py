@@ -1,4 +1,4 @@
-"""ctypes binding of libtvb.so (include/tvb.h).  Raw pointers and sizes only; no torch types cross the ABI.
+"""ctypes binding of libtvb.so (include/tvb.h, include/tvb_vocoder.h).  Raw pointers and sizes only; no torch types cross the ABI.
 
 The library is the product: if it is missing or cannot be loaded this module raises, it never falls back to another
 implementation.
@@ -25,6 +25,13 @@ class TvbConfig(C.Structure):
         "num_hidden_layers", "convpos_width", "convpos_groups", "convpos_depth")] + [("sigma_min", C.c_float)]
 
 
+class TvbVocConfig(C.Structure):          # include/tvb_vocoder.h: tvb_voc_config
+    _fields_ = [("num_mels", C.c_int32), ("upsample_initial_channel", C.c_int32), ("num_upsamples", C.c_int32),
+                ("upsample_rates", C.c_int32 * 8), ("upsample_kernel_sizes", C.c_int32 * 8), ("num_kernels", C.c_int32),
+                ("resblock_kernel_sizes", C.c_int32 * 4), ("resblock_dilation_sizes", (C.c_int32 * 3) * 4),
+                ("snake_logscale", C.c_int32), ("snakebeta", C.c_int32)]
+
+
 _P = C.c_void_p
 _SIGNATURES = {
     # name: (restype, argtypes)  -- must list every symbol include/tvb.h declares (tests check this)
@@ -48,6 +55,18 @@ _SIGNATURES = {
     "tvb_debug_attention": (C.c_int, [C.c_int, _P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, _P, C.c_int32, C.c_int32, _P]),
     "tvb_debug_set_trace": (C.c_int, [_P]),
+    # include/tvb_vocoder.h
+    "tvb_voc_create": (C.c_int, [C.POINTER(TvbVocConfig), C.c_int, C.POINTER(_P)]),
+    "tvb_voc_destroy": (None, [_P]),
+    "tvb_voc_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int32]),
+    "tvb_voc_finalize_weights": (C.c_int, [_P]),
+    "tvb_voc_set_precision": (C.c_int, [_P, C.c_int32]),
+    "tvb_voc_forward": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
+    "tvb_voc_debug_activation": (C.c_int, [_P, C.c_char_p, _P, C.c_int32, C.c_int32, _P, _P]),
+    "tvb_voc_kernel_launches": (C.c_int64, [_P]),
+    "tvb_voc_set_profile": (C.c_int, [_P, C.c_int32]),
+    "tvb_voc_profile_read": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int32]),
+    "tvb_voc_device_bytes": (C.c_int64, [_P]),
     "tvb_last_error": (C.c_char_p, []),
     "tvb_version": (C.c_char_p, []),
 }
