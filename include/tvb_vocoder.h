@@ -50,6 +50,10 @@ int tvb_voc_finalize_weights(tvb_voc_handle* h);
 /* tvb_precision: bf16 tcgen05 convolutions (default) or the all-fp32 CUDA-core validation path. */
 int tvb_voc_set_precision(tvb_voc_handle* h, int32_t precision);
 
+/* Ablation switches: "halo" = 1 (default: activation tile fetched once per tile, taps are row-shifted shared-memory descriptors),
+ * 0 (one activation fetch per tap). */
+int tvb_voc_set_option(tvb_voc_handle* h, const char* name, int32_t value);
+
 /* Replaces: BigVGAN.forward (models.py:192-222).  mel_dev fp32 [B, num_mels, T] (reference layout) ->
  * wav_dev fp32 [B, 1, T * prod(upsample_rates)].  Enqueues on `stream`; synchronises only when the workspace must grow. */
 int tvb_voc_forward(tvb_voc_handle* h, const float* mel_dev, int32_t B, int32_t T, float* wav_dev, void* stream);
@@ -59,7 +63,8 @@ int tvb_voc_forward(tvb_voc_handle* h, const float* mel_dev, int32_t B, int32_t 
 int tvb_voc_debug_activation(tvb_voc_handle* h, const char* name, const float* x_dev, int32_t B, int32_t T, float* out_dev, void* stream);
 
 /* Measurement: kernels launched so far; per-category device milliseconds of the last forward when profiling is on
- * (ms[0] = convolutions, ms[1] = activations, ms[2] = layout / conv_post); device bytes held (weights + workspace). */
+ * (ms[0] = convolutions, ms[1] = activations, ms[2] = layout / conv_post, then when n allows ms[3 + i] = convolutions of
+ * upsampling stage i and ms[3 + TVB_VOC_MAX_UPSAMPLES + i] = its activations); device bytes held (weights + workspace). */
 int64_t tvb_voc_kernel_launches(const tvb_voc_handle* h);
 int tvb_voc_set_profile(tvb_voc_handle* h, int32_t on);
 int tvb_voc_profile_read(tvb_voc_handle* h, float* ms, int32_t n);

@@ -83,3 +83,34 @@ def test_reconstruct_mel_runs_end_to_end_and_matches_manual_pipeline():
     e = rel_l2(out, want)
     print("reconstruct_mel vs manual pipeline rel-L2", e)
     assert e < 1e-3
+
+
+def test_reconstruct_speech_units_to_waveform_matches_oracle_chain():
+    """glue.reconstruct_speech (model_util.py:72-105): units -> mel -> wav on the GPU (both models on their fp32 validation paths)
+    against the oracle chain fed the SAME mel-stage noise: oracle Voicebox Euler solve + oracle BigVGAN forward."""
+    import numpy as np
+    from usdm_b200 import glue, BigVGAN
+    from oracle import vocoder_oracle as V
+    from util import weights, CFG, O
+    m = model(0, False, "fp32")
+    vsd = V.init_vocoder_weights(11, V.SMALL_CFG)
+    voc = BigVGAN(V.SMALL_CFG)
+    voc.load_state_dict(vsd)
+    voc = voc.cuda().eval().set_precision("fp32")
+    g = torch.Generator().manual_seed(2)
+    agent = torch.randint(0, 10000, (30,), generator=g)
+    ref_unit = torch.randint(0, 10000, (20,), generator=g)
+    ref_audio = (0.1 * torch.randn(22050, generator=g)).clamp(-1, 1)
+    torch.manual_seed(7)
+    audio = glue.reconstruct_speech(agent, m, voc, ref_audio, ref_unit, n_timesteps=2, solver="euler")
+    au, _ = G.process_unit(agent)
+    assert isinstance(audio, np.ndarray) and audio.dtype == np.float32 and audio.shape == (au.shape[-1] * 256,)
+    assert np.abs(audio).max() <= 1.0
+    # the mel the GPU path produced, then the oracle vocoder on it: isolates the mel -> wav hand-off (de-normalisation, layout, clamp)
+    torch.manual_seed(7)
+    mel = glue.reconstruct_mel(agent, m, ref_audio, ref_unit, n_timesteps=2, solver="euler")
+    want = V.bigvgan_forward(vsd, mel.cpu(), V.SMALL_CFG).squeeze().clamp(-1, 1).numpy()
+    err = float(np.linalg.norm(audio - want) / np.linalg.norm(want))
+    print("reconstruct_speech vs oracle vocoder on the same mel: rel-L2", err)
+    assert err < 1e-5
+    m.set_precision("bf16")

@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="vocoder option name=value (e.g. halo=0)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -62,6 +63,9 @@ def main():
     model = BigVGAN(h)
     random_weights(model)
     model = model.to(dev).eval().set_precision(args.precision)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        model.set_option(k, int(v))
     B, T = args.batch, frames_for_seconds(args.seconds)
     g = torch.Generator().manual_seed(1)
     mel_host = (torch.randn(B, 80, T, generator=g) * 1.2).pin_memory()
@@ -91,7 +95,7 @@ def main():
     fl = conv_flops_per_frame(h) * B * T
     peaks = load_peaks()
     line = dict(metric="vocoder_wav_samples_per_sec", value=B * T * 256 / (ms / 1e3), unit="samples/s", mel_frames_per_s=B * T / (ms / 1e3),
-                ms_per_forward=ms, n_gpus=1, steps=args.steps, dtype=args.precision, data="synthetic",
+                ms_per_forward=ms, options=args.opt, n_gpus=1, steps=args.steps, dtype=args.precision, data="synthetic",
                 config=dict(workload=f"BigVGAN 22 kHz/80-band forward, {B} x {T} frames ({args.seconds:g} s each)", params_m=sum(p.numel() for p in model.parameters()) / 1e6),
                 e2e=dict(value=B * T * 256 / (e2e_ms / 1e3), unit="samples/s", h2d_bytes_per_step=mel_host.numel() * 4, d2h_bytes_per_step=wav_host.numel() * 4),
                 gpu_launches=int(launches), conv_tflops=fl / (ms / 1e3) / 1e12, kernels_ms=prof,

@@ -5,8 +5,10 @@
 // both ends of every utterance is TMA's out-of-bounds fill on the time axis of a 3-D (channel, time, batch) tensor map, so no
 // im2col buffer exists.  A ConvTranspose1d(k = 2u, stride u, pad u/2) (models.py:158-163) is the same kernel: 3 taps and
 // N = u * C_out outputs per input step, row [u * C_out] of step t being output steps t*u .. t*u+u-1 (weights regrouped once).
-//   voc_conv_tc_kernel : tcgen05 implicit-GEMM conv; warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue, persistent,
-//                        smem operand ring + 2 TMEM accumulators; epilogue out = alpha * (acc + bias + resid) (+ out).
+//   voc_conv_halo_kernel: tcgen05 implicit-GEMM conv (default); warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue, persistent;
+//                        the activation tile is fetched once with its halo and each tap is a row-shifted smem descriptor;
+//                        2 TMEM accumulators; epilogue out = alpha * (acc + bias + resid) (+ out).
+//   voc_conv_tc_kernel : same math, one activation fetch per tap (ablation `halo = 0`, and layers whose halo exceeds 32 rows).
 //   k_voc_act          : Activation1d (alias_free_torch/act.py:21-27): x2 kaiser-sinc upsample (polyphase, replicate edges),
 //                        Snake / SnakeBeta (activations.py:40-50, :107-119), x2 low-pass downsample -- one pass, registers only.
 //   k_voc_conv_f32     : CUDA-core fp32 conv with the same epilogue (validation path, <= 1e-5 of the reference).
@@ -137,69 +139,99 @@ __global__ void k_voc_to_bf16(const float* __restrict__ x, size_t rows, int C, i
 // One thread = one channel x VOC_ACT_TT consecutive outputs; x, (v_even, v_odd) windows live in registers.
 // ------------------------------------------------------------------------------------------------------------------------------
 constexpr int VOC_ACT_TT = 64;
-struct VocFilt { float up[12]; float dn[12]; };
+struct VocFilt { float up[12]; float dn[12]; float dn_sum; };    // up[] carries the upsampler's x2 gain; dn_sum = sum(dn) (1 for the reference's filters)
 
-template <typename OutT>
+// FAST (bf16 path): sin^2 through MUFU.COS -- v = u + hb - hb * cos(2 a u), hb = inv_b / 2; the constant hb passes through the
+// unit-gain low-pass unchanged, so it is added once per output instead of once per upsampled sample.  The approximation's absolute
+// error (~|arg| * 2^-23 for the |arg| of a few tens met here) is three orders of magnitude below the bf16 rounding of the output.
+// The 7-deep x and (v_even, v_odd) windows are rings indexed by (iteration mod 7); the inner loop is unrolled by 7 so every ring
+// index is a compile-time constant and the windows never move between registers.  A chunk is exactly 10 groups of 7 iterations
+// (6 warm-up iterations + 64 outputs); chunks whose whole footprint lies inside the signal take the INTERIOR instantiation, which
+// has no index clamps, no edge branch and no per-iteration range tests (they were half of the issued instructions).
+template <typename OutT, bool FAST, bool INTERIOR>
+__device__ __forceinline__ void voc_act_chunk(const float* __restrict__ xb, OutT* __restrict__ ob, int C, int T, int ld_out, int t0, float2 ab,
+                                              const VocFilt& F) {
+    auto ldx = [&](int t) {
+        if (!INTERIOR) t = t < 0 ? 0 : (t >= T ? T - 1 : t);
+        return __ldg(xb + static_cast<size_t>(t) * C);
+    };
+    const float a2 = 2.f * ab.x, hb = 0.5f * ab.y, y0 = FAST ? hb * F.dn_sum : 0.f;
+    auto snake = [&](float u) {                      // FAST returns v - hb (see above)
+        if (FAST) return fmaf(-hb, __cosf(u * a2), u);
+        const float s = sinf(u * ab.x);
+        return fmaf(ab.y, s * s, u);
+    };
+    const int t_end = INTERIOR ? t0 + VOC_ACT_TT : min(t0 + VOC_ACT_TT, T);
+    const int q_last = t_end + 2;
+    float xr[7], ve[7], vo[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) ve[i] = vo[i] = 0.f;
+    xr[0] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xr[1 + i] = ldx(t0 - 6 + i);          // x[q-3 .. q+2] for the first q = t0 - 3 ("iterations -6 .. -1")
+    float nx[7];                                                       // the 7 samples the current group shifts in, loaded one group ahead
+#pragma unroll
+    for (int r = 0; r < 7; ++r) nx[r] = ldx(t0 + r);
+    for (int q0 = t0 - 3; q0 <= q_last; q0 += 7) {
+        float pf[7];                                                   // next group's loads are in flight while this group computes
+#pragma unroll
+        for (int r = 0; r < 7; ++r) pf[r] = ldx(q0 + 10 + r);
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+            const int q = q0 + r;
+            if (INTERIOR || q <= q_last) {
+                xr[r] = nx[r];                                            // = x[q + 3]; window x[q-3+i] = xr[(r + 1 + i) % 7]
+                float e, o;
+                if (INTERIOR || (q >= 0 && q < T)) {
+                    float ue = 0.f, uo = 0.f;
+#pragma unroll
+                    for (int m = 0; m < 6; ++m) {
+                        ue = fmaf(F.up[2 * m + 1], xr[(r + 6 - m) % 7], ue);      // x[q + 2 - m] = window[5 - m]
+                        uo = fmaf(F.up[2 * m], xr[(r + 7 - m) % 7], uo);          // x[q + 3 - m] = window[6 - m]
+                    }
+                    e = snake(ue);
+                    o = snake(uo);
+                } else {
+                    // replicate padding of v: left of 0 every position takes v[0], right of 2T-1 takes v[2T-1]
+                    const int qc = q < 0 ? 0 : T - 1;
+                    float uu = 0.f;
+#pragma unroll
+                    for (int m = 0; m < 6; ++m) uu = fmaf(q < 0 ? F.up[2 * m + 1] : F.up[2 * m], ldx(qc + (q < 0 ? 2 : 3) - m), uu);
+                    e = o = snake(uu);
+                }
+                ve[r] = e; vo[r] = o;                                     // pair q' = t - 3 + i sits in slot (r + 1 + i) % 7, t = q - 3
+                const int t = q - 3;
+                if (t >= t0 && (INTERIOR || t < t_end)) {
+                    float y = fmaf(F.dn[0], vo[(r + 1) % 7], y0);
+#pragma unroll
+                    for (int d = 1; d <= 5; ++d) {
+                        y = fmaf(F.dn[2 * d - 1], ve[(r + 1 + d) % 7], y);
+                        y = fmaf(F.dn[2 * d], vo[(r + 1 + d) % 7], y);
+                    }
+                    y = fmaf(F.dn[11], ve[r], y);
+                    ob[static_cast<size_t>(t) * ld_out] = static_cast<OutT>(y);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 7; ++r) nx[r] = pf[r];
+    }
+}
+
+// F.up arrives pre-multiplied by the upsampler's gain of 2 (resample.py:27).
+template <typename OutT, bool FAST>
 __global__ void __launch_bounds__(128)
 k_voc_act(const float* __restrict__ x, int C, int T, int ld_out, const float2* __restrict__ consts, VocFilt F, OutT* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;              // block = (channels, time chunks): 32..128 x 4..1
-    const int b = blockIdx.z, t0 = (blockIdx.y * blockDim.y + threadIdx.y) * VOC_ACT_TT;
-    if (c >= C || t0 >= T) return;
+    // flat (time chunk, channel) -> thread map: consecutive lanes take consecutive channels and wrap into the next chunk, so narrow
+    // layers (24 / 48 channels) still fill every lane and a warp's load is at most two contiguous runs
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = gid % C, t0 = (gid / C) * VOC_ACT_TT, b = blockIdx.y;
+    if (t0 >= T) return;
     const float* xb = x + static_cast<size_t>(b) * T * C + c;
     OutT* ob = out + static_cast<size_t>(b) * T * ld_out + c;
     const float2 ab = consts[c];
-    auto ldx = [&](int t) { t = t < 0 ? 0 : (t >= T ? T - 1 : t); return __ldg(xb + static_cast<size_t>(t) * C); };
-    // x window xw[i] = x[q - 3 + i], i = 0..6, for the current q
-    float xw[7];
-    int q = t0 - 3;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) xw[i + 1] = ldx(q - 3 + i);       // shifted in below
-    float ve[7], vo[7];                                            // (v[2q'], v[2q'+1]) for q' = q-6 .. q
-#pragma unroll
-    for (int i = 0; i < 7; ++i) ve[i] = vo[i] = 0.f;
-    const int t_end = min(t0 + VOC_ACT_TT, T);
-    for (; q <= t_end + 2; ++q) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) xw[i] = xw[i + 1];
-        xw[6] = ldx(q + 3);
-        // replicate padding of v: positions left of 0 take v[0], right of 2T-1 take v[2T-1]; evaluate at the clamped q
-        float e, o;
-        if (q >= 0 && q < T) {
-            float ue = 0.f, uo = 0.f;
-#pragma unroll
-            for (int m = 0; m < 6; ++m) {
-                ue = fmaf(F.up[2 * m + 1], xw[5 - m], ue);         // x[q + 2 - m] = xw[5 - m]
-                uo = fmaf(F.up[2 * m], xw[6 - m], uo);             // x[q + 3 - m] = xw[6 - m]
-            }
-            ue *= 2.f; uo *= 2.f;
-            const float se = sinf(ue * ab.x), so = sinf(uo * ab.x);
-            e = fmaf(ab.y, se * se, ue);
-            o = fmaf(ab.y, so * so, uo);
-        } else {
-            // outside the signal: recompute the edge sample (q = 0 even phase, or q = T-1 odd phase) from the clamped window
-            const int qc = q < 0 ? 0 : T - 1;
-            float uu = 0.f;
-#pragma unroll
-            for (int m = 0; m < 6; ++m) uu = fmaf(q < 0 ? F.up[2 * m + 1] : F.up[2 * m], ldx(qc + (q < 0 ? 2 : 3) - m), uu);
-            uu *= 2.f;
-            const float s = sinf(uu * ab.x);
-            e = o = fmaf(ab.y, s * s, uu);
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { ve[i] = ve[i + 1]; vo[i] = vo[i + 1]; }
-        ve[6] = e; vo[6] = o;
-        const int t = q - 3;                                       // window now holds q' = t-3 .. t+3
-        if (t >= t0 && t < t_end) {
-            float y = F.dn[0] * vo[0];
-#pragma unroll
-            for (int d = 1; d <= 5; ++d) {
-                y = fmaf(F.dn[2 * d - 1], ve[d], y);
-                y = fmaf(F.dn[2 * d], vo[d], y);
-            }
-            y = fmaf(F.dn[11], ve[6], y);
-            ob[static_cast<size_t>(t) * ld_out] = static_cast<OutT>(y);
-        }
-    }
+    if (t0 >= 6 && t0 + VOC_ACT_TT + 16 <= T) voc_act_chunk<OutT, FAST, true>(xb, ob, C, T, ld_out, t0, ab, F);
+    else voc_act_chunk<OutT, FAST, false>(xb, ob, C, T, ld_out, t0, ab, F);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
@@ -260,11 +292,17 @@ k_voc_conv_f32(const float* __restrict__ x, const float* __restrict__ wt, VocCon
 constexpr int VC_BM = 128;
 constexpr int VC_A_BYTES = VC_BM * 64 * 2;
 constexpr int VC_THREADS = 192;
+// ACC_COLS = TMEM columns per accumulator (>= the layer's N tile).  Wide layers (N tile > 128) run one CTA per SM with a 4-deep ring;
+// narrow layers (the 96 .. 24-channel stages: short K loops, epilogue-bound) run 2 / 3 CTAs per SM with a 3-deep ring each, so
+// several epilogues' global-memory latencies overlap.
 template <int ACC_COLS> struct VcCfg {
-    static constexpr int kStages = ACC_COLS > 64 ? 4 : 6;
+    static constexpr int kStages = ACC_COLS > 128 ? 4 : 3;
+    static constexpr int kMinBlocks = ACC_COLS > 128 ? 1 : (ACC_COLS > 64 ? 2 : 3);
     static constexpr int kBBytes = ACC_COLS * 64 * 2;
     static constexpr int kStageBytes = VC_A_BYTES + kBBytes;
     static constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
+    static_assert(kMinBlocks * (kSmem + 1024) <= 232448, "shared memory of the co-resident CTAs");
+    static_assert(kMinBlocks * 2 * ACC_COLS <= 512, "TMEM of the co-resident CTAs");
 };
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2) {
@@ -275,8 +313,59 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
-template <int ACC_COLS>        // TMEM columns per accumulator (>= bn): 256 or 64
-__global__ void __launch_bounds__(VC_THREADS, 1)
+// One epilogue warp's 32 rows of a (128 x bn) accumulator: out = alpha * (acc + bias + resid) (+ out), 16 columns at a time.
+__device__ __forceinline__ void voc_epilogue_rows(const VocConvParams& p, uint32_t acc_tmem, int quad, int lane, int nt, int mt, int b, bool vec) {
+    const int t = mt * VC_BM + quad * 32 + lane;
+    const bool row_ok = t < p.T;
+    const size_t row_off = (static_cast<size_t>(b) * p.T + (row_ok ? t : 0)) * p.N;
+#pragma unroll 1
+    for (int c = 0; c < p.bn / 16; ++c) {
+        const int n0 = nt * p.bn + c * 16;
+        const bool live = row_ok && n0 < p.N;
+        // the residual / running-sum operands do not depend on the accumulator: get them in flight before waiting on TMEM
+        float4 rq[4], oq[4];
+        if (vec && live) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + 4 * j;
+                rq[j] = (p.resid && n < p.N) ? *reinterpret_cast<const float4*>(p.resid + row_off + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                oq[j] = (p.accumulate && n < p.N) ? *reinterpret_cast<const float4*>(p.out + row_off + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        uint32_t r[16];
+        tmem_ld_32x16(acc_tmem + (static_cast<uint32_t>(quad * 32) << 16) + c * 16, r);
+        tmem_ld_wait();
+        if (!live) continue;
+        if (vec) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + 4 * j;
+                if (n >= p.N) break;
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                float4 v = make_float4((__uint_as_float(r[4 * j]) + bv.x + rq[j].x) * p.alpha + oq[j].x,
+                                       (__uint_as_float(r[4 * j + 1]) + bv.y + rq[j].y) * p.alpha + oq[j].y,
+                                       (__uint_as_float(r[4 * j + 2]) + bv.z + rq[j].z) * p.alpha + oq[j].z,
+                                       (__uint_as_float(r[4 * j + 3]) + bv.w + rq[j].w) * p.alpha + oq[j].w);
+                *reinterpret_cast<float4*>(p.out + row_off + n) = v;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = n0 + j;
+                if (n < p.N) {
+                    float v = __uint_as_float(r[j]) + p.bias[n];
+                    if (p.resid) v += p.resid[row_off + n];
+                    v *= p.alpha;
+                    if (p.accumulate) v += p.out[row_off + n];
+                    p.out[row_off + n] = v;
+                }
+            }
+        }
+    }
+}
+
+template <int ACC_COLS>        // 256, 128 or 64
+__global__ void __launch_bounds__(VC_THREADS, VcCfg<ACC_COLS>::kMinBlocks)
 voc_conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, VocConvParams p) {
     using Cfg = VcCfg<ACC_COLS>;
     extern __shared__ uint8_t smem_raw[];
@@ -353,50 +442,140 @@ voc_conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             const int nt = tile % n_tiles, mt = (tile / n_tiles) % m_tiles, b = tile / (n_tiles * m_tiles);
             mbar_wait(&tfull_bar[as], (it >> 1) & 1);
             tc_fence_after();
-            const int t = mt * VC_BM + quad * 32 + lane;
-            const bool row_ok = t < p.T;
-            const size_t row_off = (static_cast<size_t>(b) * p.T + (row_ok ? t : 0)) * p.N;
-#pragma unroll 1
-            for (int c = 0; c < p.bn / 16; ++c) {
-                uint32_t r[16];
-                tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * ACC_COLS + c * 16, r);
-                tmem_ld_wait();
-                const int n0 = nt * p.bn + c * 16;
-                if (!row_ok || n0 >= p.N) continue;
-                if (vec) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int n = n0 + 4 * j;
-                        if (n >= p.N) break;
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                        float4 v = make_float4(__uint_as_float(r[4 * j]) + bv.x, __uint_as_float(r[4 * j + 1]) + bv.y,
-                                               __uint_as_float(r[4 * j + 2]) + bv.z, __uint_as_float(r[4 * j + 3]) + bv.w);
-                        if (p.resid) {
-                            const float4 q = *reinterpret_cast<const float4*>(p.resid + row_off + n);
-                            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-                        }
-                        v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
-                        float4* o = reinterpret_cast<float4*>(p.out + row_off + n);
-                        if (p.accumulate) { const float4 q = *o; v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
-                        *o = v;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = n0 + j;
-                        if (n < p.N) {
-                            float v = __uint_as_float(r[j]) + p.bias[n];
-                            if (p.resid) v += p.resid[row_off + n];
-                            v *= p.alpha;
-                            if (p.accumulate) v += p.out[row_off + n];
-                            p.out[row_off + n] = v;
-                        }
-                    }
-                }
-            }
+            voc_epilogue_rows(p, tmem_base + as * ACC_COLS, quad, lane, nt, mt, b, vec);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 2) {
+        tc_fence_after();
+        tmem_dealloc<2 * ACC_COLS>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// Halo variant (default): the activation tile is fetched ONCE per (tile, 64-channel chunk) with its halo --
+// rows [t0 - halo, t0 + 128 + halo), halo = (taps / 2) * dilation <= 32 -- and every tap's MMA reads it through a shared-memory
+// descriptor whose start address is advanced by tap * dilation rows (128 B each; the 128-byte swizzle is a function of the
+// absolute shared-memory address, so a row-shifted start sees the tile exactly as TMA laid it out).  Per tile this replaces
+// `taps` 16 KB activation fetches by one <= 24 KB fetch: 3-11x less L2 -> SM traffic, which is what bounds the narrow
+// (96 .. 24-channel) stages.  Two rings: 2 activation slots (24 KB) and 3-4 weight slots (bn x 128 B).
+// ------------------------------------------------------------------------------------------------------------------------------
+constexpr int VH_A_ROWS = 192;
+constexpr int VH_A_BYTES = VH_A_ROWS * 128;        // 24 KB
+constexpr int VH_A_SLOTS = 2;
+template <int ACC_COLS> struct VhCfg {
+    static constexpr int kWStages = ACC_COLS > 128 ? 4 : 3;
+    static constexpr int kMinBlocks = ACC_COLS > 128 ? 1 : (ACC_COLS > 64 ? 2 : 3);
+    static constexpr int kWBytes = ACC_COLS * 64 * 2;
+    static constexpr int kSmemW = VH_A_SLOTS * VH_A_BYTES;
+    static constexpr int kSmemBar = kSmemW + kWStages * kWBytes;
+    static constexpr int kSmem = kSmemBar + 1024 + 256;
+    static_assert(kMinBlocks * (kSmem + 1024) <= 232448, "shared memory of the co-resident CTAs");
+    static_assert(kMinBlocks * 2 * ACC_COLS <= 512, "TMEM of the co-resident CTAs");
+};
+
+template <int ACC_COLS>
+__global__ void __launch_bounds__(VC_THREADS, VhCfg<ACC_COLS>::kMinBlocks)
+voc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX /* box 64 x a_rows x 1 */, const __grid_constant__ CUtensorMap tmW, VocConvParams p,
+                     int a_rows) {
+    using Cfg = VhCfg<ACC_COLS>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + Cfg::kSmemBar);
+    uint64_t* a_empty = a_full + VH_A_SLOTS;
+    uint64_t* w_full = a_empty + VH_A_SLOTS;
+    uint64_t* w_empty = w_full + Cfg::kWStages;
+    uint64_t* tfull_bar = w_empty + Cfg::kWStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (p.T + VC_BM - 1) / VC_BM, n_tiles = p.n_pad / p.bn;
+    const int num_tiles = p.B * m_tiles * n_tiles;
+    const int kc = p.ci_pad / 64;
+    const int halo = (p.taps / 2) * p.dil;
+    const uint32_t a_tx = static_cast<uint32_t>(a_rows) * 128u, w_tx = static_cast<uint32_t>(p.bn) * 128u;
+
+    if (warp_idx == 0 && lane == 0) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW); }
+    if (warp_idx == 1 && lane == 0) {
+        for (int s = 0; s < VH_A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < Cfg::kWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp_idx == 2) tmem_alloc<2 * ACC_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp_idx == 0) {
+        if (elect_one()) {
+            int as = 0, ws = 0; uint32_t aph = 0, wph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % n_tiles, mt = (tile / n_tiles) % m_tiles, b = tile / (n_tiles * m_tiles);
+                for (int c = 0; c < kc; ++c) {
+                    mbar_wait(&a_empty[as], aph ^ 1);
+                    mbar_arrive_expect_tx(&a_full[as], a_tx);
+                    tma_load_3d(smem + as * VH_A_BYTES, &tmX, &a_full[as], c * 64, mt * VC_BM - halo, b);
+                    if (++as == VH_A_SLOTS) { as = 0; aph ^= 1; }
+                    for (int tap = 0; tap < p.taps; ++tap) {
+                        mbar_wait(&w_empty[ws], wph ^ 1);
+                        mbar_arrive_expect_tx(&w_full[ws], w_tx);
+                        tma_load_2d(smem + Cfg::kSmemW + ws * Cfg::kWBytes, &tmW, &w_full[ws], tap * p.ci_pad + c * 64, nt * p.bn);
+                        if (++ws == Cfg::kWStages) { ws = 0; wph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(128, p.bn);
+            int as = 0, ws = 0; uint32_t aph = 0, wph = 0; int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+                for (int c = 0; c < kc; ++c) {
+                    mbar_wait(&a_full[as], aph);
+                    const uint32_t sa0 = smem_u32(smem + as * VH_A_BYTES);
+                    for (int tap = 0; tap < p.taps; ++tap) {
+                        mbar_wait(&w_full[ws], wph);
+                        tc_fence_after();
+                        const uint32_t sa = sa0 + static_cast<uint32_t>(tap * p.dil) * 128u;       // row shift = tap * dilation
+                        // measured on B200: the descriptor's base-offset field must stay 0 here (the pattern start is 1024-aligned);
+                        // setting it to the start row's phase breaks the result
+                        const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+                        const uint64_t db = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemW + ws * Cfg::kWBytes), 16, 1024);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (c | tap | k) != 0);
+                        umma_commit(&w_empty[ws]);
+                        if (++ws == Cfg::kWStages) { ws = 0; wph ^= 1; }
+                    }
+                    umma_commit(&a_empty[as]);
+                    if (++as == VH_A_SLOTS) { as = 0; aph ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);
+            }
+        }
+    } else {
+        const int quad = warp_idx & 3;
+        const bool vec = (p.N & 3) == 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const int nt = tile % n_tiles, mt = (tile / n_tiles) % m_tiles, b = tile / (n_tiles * m_tiles);
+            mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+            tc_fence_after();
+            voc_epilogue_rows(p, tmem_base + acc * ACC_COLS, quad, lane, nt, mt, b, vec);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
     }
     tc_fence_before();

@@ -36,11 +36,13 @@ struct tvb_voc_handle {
     float *X = nullptr, *XS = nullptr, *U = nullptr, *R = nullptr, *Hb = nullptr, *AF = nullptr;
     bf16* A16 = nullptr;
     // profiling
+    int opt_halo = 1;                             // 1 = halo kernel (activation tile fetched once per tile), 0 = one fetch per tap
     bool profile = false;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_cat;
     size_t ev_used = 0;
-    float prof_ms[3] = {0.f, 0.f, 0.f};
+    int cur_stage = -1;                           // upsampling stage being enqueued (profiling split)
+    float prof_ms[3 + 2 * TVB_VOC_MAX_UPSAMPLES] = {};   // [0..2] conv / activation / other, then conv per stage, activation per stage
 };
 
 struct VocProf {
@@ -54,7 +56,7 @@ struct VocProf {
             cudaEventCreate(&e);
             h->ev_pool.push_back(e);
         }
-        h->ev_cat.push_back(cat);
+        h->ev_cat.push_back(cat | ((h->cur_stage + 1) << 8));
         cudaEventRecord(h->ev_pool[h->ev_used], st);
     }
     ~VocProf() {
@@ -84,11 +86,11 @@ static void voc_free_bag(std::vector<void*>& bag) {
 
 // 3-D (channel, time, batch) bf16 map over a time-major activation buffer [B][T][ld]; box 64 x 128 x 1, 128-byte swizzle.
 // Rows outside [0, T) and channels outside [0, C) read as zero: this IS the convolution's zero padding.
-static int make_tmap_act3(CUtensorMap* m, const void* ptr, int C, int ld, int T, int B) {
+static int make_tmap_act3(CUtensorMap* m, const void* ptr, int C, int ld, int T, int B, int box_rows = 128) {
     TRY(resolve_driver());
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
     cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(T) * ld * 2};
-    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -276,6 +278,11 @@ static int voc_make_act(tvb_voc_handle* h, const std::string& name, int C) {
     CKL();
     TRY(voc_filter(h, name + ".upsample.filter", a.F.up));
     TRY(voc_filter(h, name + ".downsample.lowpass.filter", a.F.dn));
+    a.F.dn_sum = 0.f;
+    for (int i = 0; i < 12; ++i) {
+        a.F.up[i] *= 2.f;                 // UpSample1d multiplies by its ratio (resample.py:27); exact in fp32
+        a.F.dn_sum += a.F.dn[i];
+    }
     h->acts[name] = a;
     return TVB_OK;
 }
@@ -319,7 +326,11 @@ extern "C" int tvb_voc_finalize_weights(tvb_voc_handle* h) {
     static bool attr = false;
     if (!attr) {
         CK(cudaFuncSetAttribute(voc_conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, VcCfg<256>::kSmem));
+        CK(cudaFuncSetAttribute(voc_conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, VcCfg<128>::kSmem));
         CK(cudaFuncSetAttribute(voc_conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, VcCfg<64>::kSmem));
+        CK(cudaFuncSetAttribute(voc_conv_halo_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, VhCfg<256>::kSmem));
+        CK(cudaFuncSetAttribute(voc_conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, VhCfg<128>::kSmem));
+        CK(cudaFuncSetAttribute(voc_conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, VhCfg<64>::kSmem));
         attr = true;
     }
     h->finalized = true;
@@ -360,14 +371,13 @@ static int voc_act(tvb_voc_handle* h, const std::string& name, const float* x, i
     auto it = h->acts.find(name);
     if (it == h->acts.end()) return fail(TVB_ERR_STATE, "no activation %s", name.c_str());
     const VocActW& a = it->second;
-    const int bx = std::min(128, round_up(a.C, 32)), by = 128 / bx;
     const int chunks = (T + VOC_ACT_TT - 1) / VOC_ACT_TT;
-    dim3 block(bx, by), grid((a.C + bx - 1) / bx, (chunks + by - 1) / by, B);
+    dim3 block(128), grid(static_cast<unsigned>((static_cast<long long>(chunks) * a.C + 127) / 128), B);
     VocProf ps(h, st, 1);
     if (h->precision == TVB_PRECISION_BF16 && !force_f32)
-        k_voc_act<bf16><<<grid, block, 0, st>>>(x, a.C, T, round_up(a.C, 8), a.consts, a.F, h->A16);
+        k_voc_act<bf16, true><<<grid, block, 0, st>>>(x, a.C, T, round_up(a.C, 8), a.consts, a.F, h->A16);
     else
-        k_voc_act<float><<<grid, block, 0, st>>>(x, a.C, T, a.C, a.consts, a.F, h->AF);
+        k_voc_act<float, false><<<grid, block, 0, st>>>(x, a.C, T, a.C, a.consts, a.F, h->AF);
     CKL();
     return TVB_OK;
 }
@@ -381,11 +391,25 @@ static int voc_conv(tvb_voc_handle* h, const VocConv& L, const float* in32, int 
     VocProf ps(h, st, 0);
     if (h->precision == TVB_PRECISION_BF16) {
         CUtensorMap tmX;
-        TRY(make_tmap_act3(&tmX, h->A16, L.Cin, round_up(L.Cin, 8), T, B));
         const int tiles = B * ((T + VC_BM - 1) / VC_BM) * (L.n_pad / L.bn);
-        const int grid = std::min(tiles, h->num_sms);
-        if (L.bn > 64) voc_conv_tc_kernel<256><<<grid, VC_THREADS, VcCfg<256>::kSmem, st>>>(tmX, L.tmW, p);
-        else voc_conv_tc_kernel<64><<<grid, VC_THREADS, VcCfg<64>::kSmem, st>>>(tmX, L.tmW, p);
+        const int a_rows = round_up(VC_BM + 2 * (L.taps / 2) * L.dil, 8);
+        if (h->opt_halo && a_rows <= VH_A_ROWS) {
+            TRY(make_tmap_act3(&tmX, h->A16, L.Cin, round_up(L.Cin, 8), T, B, a_rows));
+            if (L.bn > 128)
+                voc_conv_halo_kernel<256><<<std::min(tiles, h->num_sms * VhCfg<256>::kMinBlocks), VC_THREADS, VhCfg<256>::kSmem, st>>>(tmX, L.tmW, p, a_rows);
+            else if (L.bn > 64)
+                voc_conv_halo_kernel<128><<<std::min(tiles, h->num_sms * VhCfg<128>::kMinBlocks), VC_THREADS, VhCfg<128>::kSmem, st>>>(tmX, L.tmW, p, a_rows);
+            else
+                voc_conv_halo_kernel<64><<<std::min(tiles, h->num_sms * VhCfg<64>::kMinBlocks), VC_THREADS, VhCfg<64>::kSmem, st>>>(tmX, L.tmW, p, a_rows);
+        } else {
+            TRY(make_tmap_act3(&tmX, h->A16, L.Cin, round_up(L.Cin, 8), T, B));
+            if (L.bn > 128)
+                voc_conv_tc_kernel<256><<<std::min(tiles, h->num_sms * VcCfg<256>::kMinBlocks), VC_THREADS, VcCfg<256>::kSmem, st>>>(tmX, L.tmW, p);
+            else if (L.bn > 64)
+                voc_conv_tc_kernel<128><<<std::min(tiles, h->num_sms * VcCfg<128>::kMinBlocks), VC_THREADS, VcCfg<128>::kSmem, st>>>(tmX, L.tmW, p);
+            else
+                voc_conv_tc_kernel<64><<<std::min(tiles, h->num_sms * VcCfg<64>::kMinBlocks), VC_THREADS, VcCfg<64>::kSmem, st>>>(tmX, L.tmW, p);
+        }
     } else {
         dim3 grid((T + 3) / 4, (L.N + 127) / 128, B);
         k_voc_conv_f32<<<grid, 128, 0, st>>>(in32, L.wt, p);
@@ -417,6 +441,7 @@ extern "C" int tvb_voc_forward(tvb_voc_handle* h, const float* mel_dev, int32_t 
     int Tc = T, ch = c.upsample_initial_channel;
     const float inv_k = 1.0f / static_cast<float>(c.num_kernels);
     for (int i = 0; i < c.num_upsamples; ++i) {
+        h->cur_stage = i;
         if (tc) {
             const size_t rows = static_cast<size_t>(B) * Tc;
             VocProf ps(h, st, 2);
@@ -440,6 +465,7 @@ extern "C" int tvb_voc_forward(tvb_voc_handle* h, const float* mel_dev, int32_t 
         }
         std::swap(X, XS);                                                                        // x = xs / num_kernels (models.py:209)
     }
+    h->cur_stage = -1;
     TRY(voc_act(h, "activation_post", X, B, Tc, st, true));                                      // models.py:212
     {
         VocProf ps(h, st, 2);
@@ -449,11 +475,13 @@ extern "C" int tvb_voc_forward(tvb_voc_handle* h, const float* mel_dev, int32_t 
     }
     if (h->profile) {
         CK(cudaStreamSynchronize(st));
-        h->prof_ms[0] = h->prof_ms[1] = h->prof_ms[2] = 0.f;
+        for (float& v : h->prof_ms) v = 0.f;
         for (size_t e = 0; e < h->ev_cat.size(); ++e) {
             float ms = 0.f;
             CK(cudaEventElapsedTime(&ms, h->ev_pool[2 * e], h->ev_pool[2 * e + 1]));
-            h->prof_ms[h->ev_cat[e]] += ms;
+            const int cat = h->ev_cat[e] & 0xff, stage = (h->ev_cat[e] >> 8) - 1;
+            h->prof_ms[cat] += ms;
+            if (stage >= 0 && cat < 2) h->prof_ms[3 + cat * TVB_VOC_MAX_UPSAMPLES + stage] += ms;
         }
     }
     return TVB_OK;
@@ -479,6 +507,12 @@ extern "C" int tvb_voc_debug_activation(tvb_voc_handle* h, const char* name, con
     return TVB_OK;
 }
 
+extern "C" int tvb_voc_set_option(tvb_voc_handle* h, const char* name, int32_t value) {
+    if (!h || !name) return fail(TVB_ERR_INVALID, "null argument");
+    if (!strcmp(name, "halo")) h->opt_halo = value;
+    else return fail(TVB_ERR_INVALID, "unknown vocoder option %s", name);
+    return TVB_OK;
+}
 extern "C" int64_t tvb_voc_kernel_launches(const tvb_voc_handle* h) { return h ? h->launches : 0; }
 extern "C" int64_t tvb_voc_device_bytes(const tvb_voc_handle* h) { return h ? static_cast<int64_t>(h->dev_bytes + h->ws_bytes) : 0; }
 extern "C" int tvb_voc_set_profile(tvb_voc_handle* h, int32_t on) {
@@ -487,7 +521,7 @@ extern "C" int tvb_voc_set_profile(tvb_voc_handle* h, int32_t on) {
     return TVB_OK;
 }
 extern "C" int tvb_voc_profile_read(tvb_voc_handle* h, float* ms, int32_t n) {
-    if (!h || !ms || n < 3) return fail(TVB_ERR_INVALID, "need room for 3 categories");
-    for (int i = 0; i < 3; ++i) ms[i] = h->prof_ms[i];
+    if (!h || !ms || n < 3) return fail(TVB_ERR_INVALID, "need room for at least 3 categories");
+    for (int i = 0; i < n && i < 3 + 2 * TVB_VOC_MAX_UPSAMPLES; ++i) ms[i] = h->prof_ms[i];
     return TVB_OK;
 }

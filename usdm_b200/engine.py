@@ -61,6 +61,7 @@ _SIGNATURES = {
     "tvb_voc_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int32]),
     "tvb_voc_finalize_weights": (C.c_int, [_P]),
     "tvb_voc_set_precision": (C.c_int, [_P, C.c_int32]),
+    "tvb_voc_set_option": (C.c_int, [_P, C.c_char_p, C.c_int32]),
     "tvb_voc_forward": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     "tvb_voc_debug_activation": (C.c_int, [_P, C.c_char_p, _P, C.c_int32, C.c_int32, _P, _P]),
     "tvb_voc_kernel_launches": (C.c_int64, [_P]),

@@ -152,3 +152,13 @@ def reconstruct_mel(agent_unit, voicebox, reference_audio=None, reference_unit=N
         y = voicebox.generate(agent, dummy_y, torch.tensor([T]), n_timesteps=n_timesteps, solver=solver, gradient_scale=gradient_scale,
                               speech_prompt=False)
     return y * mel_std + mel_mean
+
+
+@torch.inference_mode()
+def reconstruct_speech(agent_unit, voicebox, vocoder, reference_audio=None, reference_unit=None, n_timesteps: int = 50, hps=DEFAULT_HPS,
+                       device="cuda", solver: str = "heun", gradient_scale: float = 1.0):
+    """reconstruct_speech (model_util.py:72-105) end to end on the B200: units -> mel (usdm_b200.Voicebox) -> waveform
+    (usdm_b200.vocoder.BigVGAN), returned like the reference as a clamped float32 numpy array [T_agent * hop]."""
+    y_dec = reconstruct_mel(agent_unit, voicebox, reference_audio, reference_unit, n_timesteps, hps, device, solver, gradient_scale)
+    return vocoder.forward(y_dec).cpu().squeeze().clamp(-1, 1).numpy()          # model_util.py:104
+

@@ -121,6 +121,7 @@ class BigVGAN(nn.Module, PyTorchModelHubMixin):
         self._handle_device: Optional[int] = None
         self._weights_version = 0
         self._uploaded_version = -1
+        self._options: dict = {}
         self._extra_state: dict = {}          # weight_g / weight_v tensors kept verbatim when a weight-normed checkpoint is loaded
 
     # ------------------------------------------------------------------ reference API
@@ -150,6 +151,12 @@ class BigVGAN(nn.Module, PyTorchModelHubMixin):
         self._precision = {"bf16": E.PRECISION_BF16, "fp32": E.PRECISION_FP32_VALIDATE}[precision]
         if self._handle is not None:
             E.check(E.load_library().tvb_voc_set_precision(self._handle, self._precision))
+        return self
+
+    def set_option(self, name: str, value: int) -> "BigVGAN":
+        self._options[name] = int(value)
+        if self._handle is not None:
+            E.check(E.load_library().tvb_voc_set_option(self._handle, name.encode(), int(value)))
         return self
 
     def _config(self) -> E.TvbVocConfig:
@@ -199,6 +206,8 @@ class BigVGAN(nn.Module, PyTorchModelHubMixin):
                     E.check(lib.tvb_voc_load_weight(hd, key.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()))
                 E.check(lib.tvb_voc_finalize_weights(hd))
                 E.check(lib.tvb_voc_set_precision(hd, self._precision))
+                for k, v in self._options.items():
+                    E.check(lib.tvb_voc_set_option(hd, k.encode(), v))
             except Exception:
                 self._release()
                 raise
@@ -234,9 +243,11 @@ class BigVGAN(nn.Module, PyTorchModelHubMixin):
             E.check(E.load_library().tvb_voc_set_profile(self._handle, int(on)))
 
     def read_profile(self) -> dict:
-        ms = (C.c_float * 3)()
-        E.check(E.load_library().tvb_voc_profile_read(self._handle, ms, 3))
-        return dict(conv=ms[0], activation=ms[1], other=ms[2])
+        ms = (C.c_float * 19)()
+        E.check(E.load_library().tvb_voc_profile_read(self._handle, ms, 19))
+        n = self.num_upsamples
+        return dict(conv=ms[0], activation=ms[1], other=ms[2], conv_by_stage=[ms[3 + i] for i in range(n)],
+                    activation_by_stage=[ms[11 + i] for i in range(n)])
 
     def kernel_launches(self) -> int:
         return 0 if self._handle is None else int(E.load_library().tvb_voc_kernel_launches(self._handle))
