@@ -14,6 +14,8 @@
 //   k_voc_conv_f32     : CUDA-core fp32 conv with the same epilogue (validation path, <= 1e-5 of the reference).
 //   k_voc_post         : conv_post (C -> 1, k = 7) + tanh (models.py:217-219).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace tvb {
@@ -139,6 +141,7 @@ __global__ void k_voc_to_bf16(const float* __restrict__ x, size_t rows, int C, i
 // One thread = one channel x VOC_ACT_TT consecutive outputs; x, (v_even, v_odd) windows live in registers.
 // ------------------------------------------------------------------------------------------------------------------------------
 constexpr int VOC_ACT_TT = 64;
+static_assert((VOC_ACT_TT + 6) % 7 == 0, "a chunk must be a whole number of 7-iteration groups");
 struct VocFilt { float up[12]; float dn[12]; float dn_sum; };    // up[] carries the upsampler's x2 gain; dn_sum = sum(dn) (1 for the reference's filters)
 
 // FAST (bf16 path): sin^2 through MUFU.COS -- v = u + hb - hb * cos(2 a u), hb = inv_b / 2; the constant hb passes through the
@@ -172,10 +175,20 @@ __device__ __forceinline__ void voc_act_chunk(const float* __restrict__ xb, OutT
     float nx[7];                                                       // the 7 samples the current group shifts in, loaded one group ahead
 #pragma unroll
     for (int r = 0; r < 7; ++r) nx[r] = ldx(t0 + r);
-    for (int q0 = t0 - 3; q0 <= q_last; q0 += 7) {
+    // running pointers (interior chunks): one 64-bit add per row instead of a 64-bit multiply-add per access
+    const float* xp = xb + static_cast<size_t>(INTERIOR ? t0 + 7 : 0) * C;     // row q0 + 10 of the group being prefetched
+    OutT* op = ob + static_cast<size_t>(t0) * ld_out;                          // row of the next output
+    const size_t xstep = static_cast<size_t>(C), ostep = static_cast<size_t>(ld_out);
+
+    // one group of 7 iterations starting at q0; FIRST = the warm-up group of an interior chunk (only its last iteration has an output)
+    auto group = [&](int q0, auto first_tag) {
+        constexpr bool FIRST = decltype(first_tag)::value;
         float pf[7];                                                   // next group's loads are in flight while this group computes
 #pragma unroll
-        for (int r = 0; r < 7; ++r) pf[r] = ldx(q0 + 10 + r);
+        for (int r = 0; r < 7; ++r) {
+            if (INTERIOR) { pf[r] = __ldg(xp); xp += xstep; }
+            else pf[r] = ldx(q0 + 10 + r);
+        }
 #pragma unroll
         for (int r = 0; r < 7; ++r) {
             const int q = q0 + r;
@@ -201,7 +214,7 @@ __device__ __forceinline__ void voc_act_chunk(const float* __restrict__ xb, OutT
                 }
                 ve[r] = e; vo[r] = o;                                     // pair q' = t - 3 + i sits in slot (r + 1 + i) % 7, t = q - 3
                 const int t = q - 3;
-                if (t >= t0 && (INTERIOR || t < t_end)) {
+                if (INTERIOR ? (!FIRST || r == 6) : (t >= t0 && t < t_end)) {
                     float y = fmaf(F.dn[0], vo[(r + 1) % 7], y0);
 #pragma unroll
                     for (int d = 1; d <= 5; ++d) {
@@ -209,12 +222,20 @@ __device__ __forceinline__ void voc_act_chunk(const float* __restrict__ xb, OutT
                         y = fmaf(F.dn[2 * d], vo[(r + 1 + d) % 7], y);
                     }
                     y = fmaf(F.dn[11], ve[r], y);
-                    ob[static_cast<size_t>(t) * ld_out] = static_cast<OutT>(y);
+                    *op = static_cast<OutT>(y);
+                    op += ostep;
                 }
             }
         }
 #pragma unroll
         for (int r = 0; r < 7; ++r) nx[r] = pf[r];
+    };
+    if (INTERIOR) {
+        group(t0 - 3, std::true_type{});
+#pragma unroll 1
+        for (int g = 1; g < (VOC_ACT_TT + 6) / 7; ++g) group(t0 - 3 + 7 * g, std::false_type{});
+    } else {
+        for (int q0 = t0 - 3; q0 <= q_last; q0 += 7) group(q0, std::false_type{});
     }
 }
 

@@ -178,7 +178,7 @@ class BigVGAN(nn.Module, PyTorchModelHubMixin):
                 E.load_library().tvb_voc_destroy(self._handle)
             except Exception:
                 pass
-            self._handle = None
+            object.__setattr__(self, "_handle", None)      # plain attribute write: nn.Module.__setattr__ can fail at interpreter shutdown
 
     def __del__(self):
         self._release()
