@@ -334,7 +334,22 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// 256-bit global accesses (sm_100a): each thread owns one output row, so a warp-wide access touches 32 different rows; 32-byte
+// pieces make every transaction a whole sector (16-byte float4 accesses would be two half-sector transactions for the same data).
+struct f32x8 { float v[8]; };
+__device__ __forceinline__ f32x8 ldg256(const float* p) {
+    f32x8 r;
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg256(float* p, const f32x8& r) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]), "f"(r.v[4]),
+                 "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7]) : "memory");
+}
+
 // One epilogue warp's 32 rows of a (128 x bn) accumulator: out = alpha * (acc + bias + resid) (+ out), 16 columns at a time.
+// vec = N % 8 == 0 (every layer of the shipped model): 256-bit accesses; otherwise a scalar path (narrow test configurations).
 __device__ __forceinline__ void voc_epilogue_rows(const VocConvParams& p, uint32_t acc_tmem, int quad, int lane, int nt, int mt, int b, bool vec) {
     const int t = mt * VC_BM + quad * 32 + lane;
     const bool row_ok = t < p.T;
@@ -344,13 +359,13 @@ __device__ __forceinline__ void voc_epilogue_rows(const VocConvParams& p, uint32
         const int n0 = nt * p.bn + c * 16;
         const bool live = row_ok && n0 < p.N;
         // the residual / running-sum operands do not depend on the accumulator: get them in flight before waiting on TMEM
-        float4 rq[4], oq[4];
+        f32x8 rq[2], oq[2];
         if (vec && live) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = n0 + 4 * j;
-                rq[j] = (p.resid && n < p.N) ? *reinterpret_cast<const float4*>(p.resid + row_off + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-                oq[j] = (p.accumulate && n < p.N) ? *reinterpret_cast<const float4*>(p.out + row_off + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 2; ++j) {
+                const int n = n0 + 8 * j;
+                if (p.resid && n < p.N) rq[j] = ldg256(p.resid + row_off + n);
+                if (p.accumulate && n < p.N) oq[j] = ldg256(p.out + row_off + n);
             }
         }
         uint32_t r[16];
@@ -359,15 +374,21 @@ __device__ __forceinline__ void voc_epilogue_rows(const VocConvParams& p, uint32
         if (!live) continue;
         if (vec) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = n0 + 4 * j;
+            for (int j = 0; j < 2; ++j) {
+                const int n = n0 + 8 * j;
                 if (n >= p.N) break;
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                float4 v = make_float4((__uint_as_float(r[4 * j]) + bv.x + rq[j].x) * p.alpha + oq[j].x,
-                                       (__uint_as_float(r[4 * j + 1]) + bv.y + rq[j].y) * p.alpha + oq[j].y,
-                                       (__uint_as_float(r[4 * j + 2]) + bv.z + rq[j].z) * p.alpha + oq[j].z,
-                                       (__uint_as_float(r[4 * j + 3]) + bv.w + rq[j].w) * p.alpha + oq[j].w);
-                *reinterpret_cast<float4*>(p.out + row_off + n) = v;
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                f32x8 v;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float x = __uint_as_float(r[8 * j + e]) + bv[e];
+                    if (p.resid) x += rq[j].v[e];
+                    x *= p.alpha;
+                    if (p.accumulate) x += oq[j].v[e];
+                    v.v[e] = x;
+                }
+                stg256(p.out + row_off + n, v);
             }
         } else {
 #pragma unroll
@@ -456,7 +477,7 @@ voc_conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         }
     } else {
         const int quad = warp_idx & 3;
-        const bool vec = (p.N & 3) == 0;
+        const bool vec = (p.N & 7) == 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
@@ -586,7 +607,7 @@ voc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX /* box 64 x a_rows 
         }
     } else {
         const int quad = warp_idx & 3;
-        const bool vec = (p.N & 3) == 0;
+        const bool vec = (p.N & 7) == 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
