@@ -98,3 +98,22 @@ def test_errors():
     bad = BigVGAN(dict(V.SMALL_CFG, upsample_kernel_sizes=[8, 8, 4, 4, 4, 6]))
     with pytest.raises(ValueError):
         bad.cuda()(torch.zeros(1, 80, 8, device="cuda"))
+
+
+def test_vocode_sharded_ragged_batch_equals_per_utterance_reference_calls():
+    """parallel.vocode_sharded (world 1 here; the world-2 logic is tests/test_parallel_gloo.py): a ragged batch is vocoded
+    utterance by utterance at true length -- the reference's one-utterance call (model_util.py:104) -- not at the padded length."""
+    from usdm_b200 import parallel
+    sd = V.init_vocoder_weights(11, V.SMALL_CFG)
+    m = vocoder("small", 11, False, "fp32")
+    g = torch.Generator().manual_seed(3)
+    lens = torch.tensor([20, 7, 20, 13])
+    mel = torch.randn(4, 80, 20, generator=g) * 1.2
+    for u, t in enumerate(lens.tolist()):
+        mel[u, :, t:] = 0
+    wav = parallel.vocode_sharded(m, mel.cuda(), lens, hop=256).cpu()
+    assert wav.shape == (4, 1, 20 * 256)
+    for u, t in enumerate(lens.tolist()):
+        want = V.bigvgan_forward(sd, mel[u:u + 1, :, :t], V.SMALL_CFG)
+        assert rel_l2(wav[u:u + 1, :, :t * 256], want) < TOL_FP32
+        assert float(wav[u, :, t * 256:].abs().max()) == 0.0 if t < 20 else True

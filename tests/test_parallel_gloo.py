@@ -23,6 +23,13 @@ def _fake_generate(x, cond, lengths, **kw):
     return out * mask
 
 
+def _fake_vocode(mel):
+    """Stand-in with the BigVGAN.forward contract ([n,M,t] -> [n,1,t*4]) whose output depends on the utterance's own length
+    (like a conv stack's edge behaviour), so batching at a padded length would be detected."""
+    n, M, t = mel.shape
+    return (mel.sum(1, keepdim=True).repeat_interleave(4, dim=2) + float(t)).tanh()
+
+
 def _inputs():
     g = torch.Generator().manual_seed(7)
     lens = torch.tensor([50, 7, 33, 12, 64, 1, 20, 41, 5])
@@ -40,7 +47,8 @@ def _worker(rank, world, port, q):
         from usdm_b200 import parallel
         x, cond, lens = _inputs()
         full = parallel.generate_sharded(_fake_generate, x, cond, lens, max_tokens=150, n_timesteps=3)
-        q.put((rank, full))
+        wav = parallel.vocode_sharded(_fake_vocode, full, lens, hop=4, max_frames=60)
+        q.put((rank, (full, wav)))
     finally:
         dist.destroy_process_group()
 
@@ -70,8 +78,13 @@ def test_generate_sharded_world2_gloo_equals_single_rank():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    want_wav = torch.zeros(len(lens), 1, int(lens.max()) * 4)
+    for u, t in enumerate(lens.tolist()):
+        want_wav[u, :, :t * 4] = _fake_vocode(want[u:u + 1, :, :t])[0]
+    assert torch.equal(parallel.vocode_sharded(_fake_vocode, want, lens, hop=4, max_frames=60), want_wav)      # world 1
     for r in range(2):
-        assert torch.equal(got[r], want), f"rank {r} result differs"
+        assert torch.equal(got[r][0], want), f"rank {r} mel differs"
+        assert torch.equal(got[r][1], want_wav), f"rank {r} waveform differs"
 
 
 def test_shards_are_balanced_deterministic_and_cover_everything():

@@ -78,3 +78,46 @@ def generate_sharded(generate_fn: Callable, x: torch.Tensor, cond: torch.Tensor,
         if s:
             full[torch.tensor(s, dtype=torch.long, device=cond.device)] = gathered[r, :len(s)]
     return full
+
+
+def vocode_sharded(vocode_fn: Callable, mel: torch.Tensor, lengths: torch.Tensor, *, hop: int = 256, max_frames: int = 16000,
+                   group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Vocoder counterpart of generate_sharded: every rank calls this with the SAME mel [N, M, T] / lengths [N]; each rank runs its
+    shard through `vocode_fn` (e.g. BigVGAN.forward: [n, M, t] -> [n, 1, t * hop]) and one all-gather returns the waveforms
+    [N, 1, T * hop] (zeros past lengths * hop) on every rank.
+
+    The reference vocoder has no length argument (models.py:192): padded frames would be synthesised as content and leak into the
+    last frames of a shorter utterance through the convolutions' receptive field.  Utterances are therefore batched only with
+    others of exactly the same length, each at its true length -- what the reference's one-utterance call computes."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    N, M, T = mel.shape
+    lens = [int(v) for v in lengths.tolist()]
+    shards = shard_utterances(lens, world)
+    n_max = max(len(s) for s in shards)
+    local = torch.zeros((n_max, 1, T * hop), dtype=torch.float32, device=mel.device)
+    slot = {u: i for i, u in enumerate(shards[rank])}
+    by_len: dict = {}
+    for u in shards[rank]:
+        by_len.setdefault(lens[u], []).append(u)
+    for t, group_idx in sorted(by_len.items()):
+        if t <= 0:
+            continue
+        per_call = max(1, max_frames // t)
+        for s in range(0, len(group_idx), per_call):
+            mb = group_idx[s:s + per_call]
+            idx = torch.tensor(mb, dtype=torch.long, device=mel.device)
+            wav = vocode_fn(mel[idx][:, :, :t].contiguous())
+            for j, u in enumerate(mb):
+                local[slot[u], :, :t * hop] = wav[j]
+    if world == 1:
+        gathered = local.unsqueeze(0)
+    else:
+        flat = torch.empty((world * n_max, 1, T * hop), dtype=torch.float32, device=mel.device)
+        dist.all_gather_into_tensor(flat, local, group=group)
+        gathered = flat.view(world, n_max, 1, T * hop)
+    full = torch.zeros((N, 1, T * hop), dtype=torch.float32, device=mel.device)
+    for r, s in enumerate(shards):
+        if s:
+            full[torch.tensor(s, dtype=torch.long, device=mel.device)] = gathered[r, :len(s)]
+    return full
