@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--nfe", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-vocoder", action="store_true", help="skip the extra (untimed-region) vocoder measurement reported under `vocoder`")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (ablation), e.g. gemm_2cta=0")
     args = ap.parse_args()
     w = workload(args)
@@ -305,6 +306,34 @@ def main():
         fps, per_eval, cores, sample = cpu_reference_sample(w, 2, 1)
         cpu = dict(value=fps, unit=UNIT, cores=cores, kind="port", sample=sample)
 
+    # ---- SURVEY.md §8 row f-3, reported beside the headline (never inside its timed region): the BigVGAN forward on the mels this
+    # workload hands to the vocoder (model_util.py:94,104), and the resulting units -> waveform time of the whole batch
+    voc = None
+    if rank == 0 and world == 1 and not args.no_vocoder:
+        from usdm_b200.vocoder import BigVGAN, BIGVGAN_22K_80
+        from tools.bench_vocoder import conv_flops_per_frame, random_weights
+        vmodel = BigVGAN(BIGVGAN_22K_80)
+        random_weights(vmodel)
+        vmodel = vmodel.to(dev).eval()
+        vmel = torch.randn(w["B"], 80, w["T_target"], device=dev) * 1.2
+        for _ in range(3):
+            vmodel(vmel)
+        torch.cuda.synchronize()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = vmodel.kernel_launches()
+        v0.record()
+        for _ in range(3):
+            vmodel(vmel)
+        v1.record()
+        torch.cuda.synchronize()
+        vms = v0.elapsed_time(v1) / 3
+        solve_ms = dev_s / args.steps * 1e3
+        voc = dict(workload=f"BigVGAN 22 kHz/80-band forward on the {w['B']} x {w['T_target']} target frames of this workload (synthetic mel, random-init weights)",
+                   ms_per_forward=vms, wav_samples_per_s=w["B"] * w["T_target"] * 256 / (vms / 1e3), gpu_launches=int((vmodel.kernel_launches() - l0) // 3),
+                   conv_tflops=conv_flops_per_frame(BIGVGAN_22K_80) * w["B"] * w["T_target"] / (vms / 1e3) / 1e12,
+                   units_to_waveform_ms=solve_ms + vms, units_to_waveform_frames_per_s=w["B"] * w["T_target"] / ((solve_ms + vms) / 1e3))
+        del vmodel
+
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=dev_s / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
@@ -315,7 +344,7 @@ def main():
                     roofline_step=dict(bound="tensor", achieved=step_tflops, peak=peaks["sustained"], unit="TFLOP/s per GPU",
                                        frac=step_tflops / peaks["sustained"],
                                        note="algorithmic FLOPs of the whole solve (valid tokens) / device time"),
-                    kernels=kernels, cpu_baseline=cpu)
+                    kernels=kernels, cpu_baseline=cpu, vocoder=voc)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

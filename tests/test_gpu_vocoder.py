@@ -117,3 +117,20 @@ def test_vocode_sharded_ragged_batch_equals_per_utterance_reference_calls():
         want = V.bigvgan_forward(sd, mel[u:u + 1, :, :t], V.SMALL_CFG)
         assert rel_l2(wav[u:u + 1, :, :t * 256], want) < TOL_FP32
         assert float(wav[u, :, t * 256:].abs().max()) == 0.0 if t < 20 else True
+
+
+def test_full_model_at_maximum_length_properties():
+    """The 112 M-parameter model at BASELINE's longest utterance (20 s = 1723 frames, 441 k samples, 13.8 k time tiles in the last
+    stage): the tcgen05 path against the fp32 CUDA path, row independence and determinism -- the size-independent checks that
+    replace an oracle run the CPU cannot finish in seconds."""
+    g = torch.Generator().manual_seed(21)
+    mel = (torch.randn(2, 80, 1723, generator=g) * 1.2).cuda()
+    m = vocoder("full", 13, False, "bf16")
+    got = m(mel)
+    assert got.shape == (2, 1, 1723 * 256) and torch.isfinite(got).all()
+    assert torch.equal(got, m(mel))
+    assert torch.equal(got[1:2], m(mel[1:2]))
+    want = vocoder("full", 13, False, "fp32")(mel)
+    err = rel_l2(got, want)
+    print(f"full model, 2 x 1723 frames: bf16 vs fp32 path {err:.3e}")
+    assert err < TOL_BF16
