@@ -151,28 +151,74 @@ struct VocFilt { float up[12]; float dn[12]; float dn_sum; };    // up[] carries
 // index is a compile-time constant and the windows never move between registers.  A chunk is exactly 10 groups of 7 iterations
 // (6 warm-up iterations + 64 outputs); chunks whose whole footprint lies inside the signal take the INTERIOR instantiation, which
 // has no index clamps, no edge branch and no per-iteration range tests (they were half of the issued instructions).
-template <typename OutT, bool FAST, bool INTERIOR>
-__device__ __forceinline__ void voc_act_chunk(const float* __restrict__ xb, OutT* __restrict__ ob, int C, int T, int ld_out, int t0, float2 ab,
-                                              const VocFilt& F) {
+// VEC = 2 (bf16 path, even channel counts): one thread carries TWO adjacent channels as packed fp32 pairs -- 8-byte loads, FFMA2 for
+// both FIR filters and the snake update (the filter taps are scalar-broadcast operands of FFMA2), one 4-byte bf16x2 store --
+// which halves the issued instructions per output once more (the kernel is issue-bound, not pipe- or HBM-bound).
+__device__ __forceinline__ uint64_t vpack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void vunpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t vfma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t vmul(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+template <int VEC> struct VocLane;
+template <> struct VocLane<1> {
+    using V = float;
+    static __device__ __forceinline__ V ld(const float* p) { return __ldg(p); }
+    static __device__ __forceinline__ V fmac(float c, V x, V acc) { return fmaf(c, x, acc); }
+    static __device__ __forceinline__ V zero() { return 0.f; }
+};
+template <> struct VocLane<2> {
+    using V = uint64_t;
+    static __device__ __forceinline__ V ld(const float* p) { return __ldg(reinterpret_cast<const unsigned long long*>(p)); }
+    static __device__ __forceinline__ V fmac(float c, V x, V acc) { return vfma(vpack(c, c), x, acc); }
+    static __device__ __forceinline__ V zero() { return 0ull; }
+};
+
+template <typename OutT, bool FAST, bool INTERIOR, int VEC>
+__device__ __forceinline__ void voc_act_chunk(const float* __restrict__ xb, OutT* __restrict__ ob, int C, int T, int ld_out, int t0,
+                                              const float2* __restrict__ cst, const VocFilt& F) {
+    static_assert(VEC == 1 || FAST, "the packed variant exists for the bf16 path only");
+    using L = VocLane<VEC>;
+    using V = typename L::V;
     auto ldx = [&](int t) {
         if (!INTERIOR) t = t < 0 ? 0 : (t >= T ? T - 1 : t);
-        return __ldg(xb + static_cast<size_t>(t) * C);
+        return L::ld(xb + static_cast<size_t>(t) * C);
     };
-    const float a2 = 2.f * ab.x, hb = 0.5f * ab.y, y0 = FAST ? hb * F.dn_sum : 0.f;
-    auto snake = [&](float u) {                      // FAST returns v - hb (see above)
-        if (FAST) return fmaf(-hb, __cosf(u * a2), u);
-        const float s = sinf(u * ab.x);
-        return fmaf(ab.y, s * s, u);
+    const float2 ab = cst[0], ab1 = VEC == 2 ? cst[1] : cst[0];
+    const float a2 = 2.f * ab.x, hb = 0.5f * ab.y, a2b = 2.f * ab1.x, hbb = 0.5f * ab1.y;
+    V y0;
+    if constexpr (VEC == 2) y0 = vpack(hb * F.dn_sum, hbb * F.dn_sum);
+    else y0 = FAST ? hb * F.dn_sum : 0.f;
+    auto snake = [&](V u) -> V {                     // FAST returns v - hb (see above)
+        if constexpr (VEC == 2) {
+            float g0, g1;
+            vunpack(vmul(u, vpack(a2, a2b)), g0, g1);
+            return vfma(vpack(-hb, -hbb), vpack(__cosf(g0), __cosf(g1)), u);
+        } else {
+            if (FAST) return fmaf(-hb, __cosf(u * a2), u);
+            const float s = sinf(u * ab.x);
+            return fmaf(ab.y, s * s, u);
+        }
     };
     const int t_end = INTERIOR ? t0 + VOC_ACT_TT : min(t0 + VOC_ACT_TT, T);
     const int q_last = t_end + 2;
-    float xr[7], ve[7], vo[7];
+    V xr[7], ve[7], vo[7];
 #pragma unroll
-    for (int i = 0; i < 7; ++i) ve[i] = vo[i] = 0.f;
-    xr[0] = 0.f;
+    for (int i = 0; i < 7; ++i) ve[i] = vo[i] = L::zero();
+    xr[0] = L::zero();
 #pragma unroll
     for (int i = 0; i < 6; ++i) xr[1 + i] = ldx(t0 - 6 + i);          // x[q-3 .. q+2] for the first q = t0 - 3 ("iterations -6 .. -1")
-    float nx[7];                                                       // the 7 samples the current group shifts in, loaded one group ahead
+    V nx[7];                                                           // the 7 samples the current group shifts in, loaded one group ahead
 #pragma unroll
     for (int r = 0; r < 7; ++r) nx[r] = ldx(t0 + r);
     // running pointers (interior chunks): one 64-bit add per row instead of a 64-bit multiply-add per access
@@ -183,10 +229,10 @@ __device__ __forceinline__ void voc_act_chunk(const float* __restrict__ xb, OutT
     // one group of 7 iterations starting at q0; FIRST = the warm-up group of an interior chunk (only its last iteration has an output)
     auto group = [&](int q0, auto first_tag) {
         constexpr bool FIRST = decltype(first_tag)::value;
-        float pf[7];                                                   // next group's loads are in flight while this group computes
+        V pf[7];                                                       // next group's loads are in flight while this group computes
 #pragma unroll
         for (int r = 0; r < 7; ++r) {
-            if (INTERIOR) { pf[r] = __ldg(xp); xp += xstep; }
+            if (INTERIOR) { pf[r] = L::ld(xp); xp += xstep; }
             else pf[r] = ldx(q0 + 10 + r);
         }
 #pragma unroll
@@ -194,35 +240,41 @@ __device__ __forceinline__ void voc_act_chunk(const float* __restrict__ xb, OutT
             const int q = q0 + r;
             if (INTERIOR || q <= q_last) {
                 xr[r] = nx[r];                                            // = x[q + 3]; window x[q-3+i] = xr[(r + 1 + i) % 7]
-                float e, o;
+                V e, o;
                 if (INTERIOR || (q >= 0 && q < T)) {
-                    float ue = 0.f, uo = 0.f;
+                    V ue = L::zero(), uo = L::zero();
 #pragma unroll
                     for (int m = 0; m < 6; ++m) {
-                        ue = fmaf(F.up[2 * m + 1], xr[(r + 6 - m) % 7], ue);      // x[q + 2 - m] = window[5 - m]
-                        uo = fmaf(F.up[2 * m], xr[(r + 7 - m) % 7], uo);          // x[q + 3 - m] = window[6 - m]
+                        ue = L::fmac(F.up[2 * m + 1], xr[(r + 6 - m) % 7], ue);   // x[q + 2 - m] = window[5 - m]
+                        uo = L::fmac(F.up[2 * m], xr[(r + 7 - m) % 7], uo);       // x[q + 3 - m] = window[6 - m]
                     }
                     e = snake(ue);
                     o = snake(uo);
                 } else {
                     // replicate padding of v: left of 0 every position takes v[0], right of 2T-1 takes v[2T-1]
                     const int qc = q < 0 ? 0 : T - 1;
-                    float uu = 0.f;
+                    V uu = L::zero();
 #pragma unroll
-                    for (int m = 0; m < 6; ++m) uu = fmaf(q < 0 ? F.up[2 * m + 1] : F.up[2 * m], ldx(qc + (q < 0 ? 2 : 3) - m), uu);
+                    for (int m = 0; m < 6; ++m) uu = L::fmac(q < 0 ? F.up[2 * m + 1] : F.up[2 * m], ldx(qc + (q < 0 ? 2 : 3) - m), uu);
                     e = o = snake(uu);
                 }
                 ve[r] = e; vo[r] = o;                                     // pair q' = t - 3 + i sits in slot (r + 1 + i) % 7, t = q - 3
                 const int t = q - 3;
                 if (INTERIOR ? (!FIRST || r == 6) : (t >= t0 && t < t_end)) {
-                    float y = fmaf(F.dn[0], vo[(r + 1) % 7], y0);
+                    V y = L::fmac(F.dn[0], vo[(r + 1) % 7], y0);
 #pragma unroll
                     for (int d = 1; d <= 5; ++d) {
-                        y = fmaf(F.dn[2 * d - 1], ve[(r + 1 + d) % 7], y);
-                        y = fmaf(F.dn[2 * d], vo[(r + 1 + d) % 7], y);
+                        y = L::fmac(F.dn[2 * d - 1], ve[(r + 1 + d) % 7], y);
+                        y = L::fmac(F.dn[2 * d], vo[(r + 1 + d) % 7], y);
                     }
-                    y = fmaf(F.dn[11], ve[r], y);
-                    *op = static_cast<OutT>(y);
+                    y = L::fmac(F.dn[11], ve[r], y);
+                    if constexpr (VEC == 2) {
+                        float y_lo, y_hi;
+                        vunpack(y, y_lo, y_hi);
+                        *reinterpret_cast<__nv_bfloat162*>(op) = __floats2bfloat162_rn(y_lo, y_hi);
+                    } else {
+                        *op = static_cast<OutT>(y);
+                    }
                     op += ostep;
                 }
             }
@@ -239,20 +291,20 @@ __device__ __forceinline__ void voc_act_chunk(const float* __restrict__ xb, OutT
     }
 }
 
-// F.up arrives pre-multiplied by the upsampler's gain of 2 (resample.py:27).
-template <typename OutT, bool FAST>
+// F.up arrives pre-multiplied by the upsampler's gain of 2 (resample.py:27).  VEC = channels per thread (2 needs even C and ld_out).
+template <typename OutT, bool FAST, int VEC>
 __global__ void __launch_bounds__(128)
 k_voc_act(const float* __restrict__ x, int C, int T, int ld_out, const float2* __restrict__ consts, VocFilt F, OutT* __restrict__ out) {
     // flat (time chunk, channel) -> thread map: consecutive lanes take consecutive channels and wrap into the next chunk, so narrow
     // layers (24 / 48 channels) still fill every lane and a warp's load is at most two contiguous runs
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int c = gid % C, t0 = (gid / C) * VOC_ACT_TT, b = blockIdx.y;
+    const int cv = C / VEC;
+    const int c = (gid % cv) * VEC, t0 = (gid / cv) * VOC_ACT_TT, b = blockIdx.y;
     if (t0 >= T) return;
     const float* xb = x + static_cast<size_t>(b) * T * C + c;
     OutT* ob = out + static_cast<size_t>(b) * T * ld_out + c;
-    const float2 ab = consts[c];
-    if (t0 >= 6 && t0 + VOC_ACT_TT + 16 <= T) voc_act_chunk<OutT, FAST, true>(xb, ob, C, T, ld_out, t0, ab, F);
-    else voc_act_chunk<OutT, FAST, false>(xb, ob, C, T, ld_out, t0, ab, F);
+    if (t0 >= 6 && t0 + VOC_ACT_TT + 16 <= T) voc_act_chunk<OutT, FAST, true, VEC>(xb, ob, C, T, ld_out, t0, consts + c, F);
+    else voc_act_chunk<OutT, FAST, false, VEC>(xb, ob, C, T, ld_out, t0, consts + c, F);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
@@ -350,12 +402,13 @@ __device__ __forceinline__ void stg256(float* p, const f32x8& r) {
 
 // One epilogue warp's 32 rows of a (128 x bn) accumulator: out = alpha * (acc + bias + resid) (+ out), 16 columns at a time.
 // vec = N % 8 == 0 (every layer of the shipped model): 256-bit accesses; otherwise a scalar path (narrow test configurations).
-__device__ __forceinline__ void voc_epilogue_rows(const VocConvParams& p, uint32_t acc_tmem, int quad, int lane, int nt, int mt, int b, bool vec) {
+__device__ __forceinline__ void voc_epilogue_rows(const VocConvParams& p, uint32_t acc_tmem, int quad, int lane, int nt, int mt, int b, bool vec,
+                                                  int cset = 0, int nsets = 1) {
     const int t = mt * VC_BM + quad * 32 + lane;
     const bool row_ok = t < p.T;
     const size_t row_off = (static_cast<size_t>(b) * p.T + (row_ok ? t : 0)) * p.N;
 #pragma unroll 1
-    for (int c = 0; c < p.bn / 16; ++c) {
+    for (int c = cset; c < p.bn / 16; c += nsets) {       // `nsets` warps share a lane quarter and interleave its 16-column chunks
         const int n0 = nt * p.bn + c * 16;
         const bool live = row_ok && n0 < p.N;
         // the residual / running-sum operands do not depend on the accumulator: get them in flight before waiting on TMEM
@@ -510,6 +563,10 @@ constexpr int VH_A_ROWS = 192;
 constexpr int VH_A_BYTES = VH_A_ROWS * 128;        // 24 KB
 constexpr int VH_A_SLOTS = 2;
 template <int ACC_COLS> struct VhCfg {
+    // wide tiles run one CTA per SM, so their epilogue gets two warps per TMEM lane quarter (8 epilogue warps); the multi-CTA
+    // narrow variants keep 4 (their parallelism comes from the co-resident CTAs, and registers are the limit there)
+    static constexpr int kEpiSets = ACC_COLS > 128 ? 2 : 1;
+    static constexpr int kThreads = 64 + 128 * kEpiSets;
     static constexpr int kWStages = ACC_COLS > 128 ? 4 : 3;
     static constexpr int kMinBlocks = ACC_COLS > 128 ? 1 : (ACC_COLS > 64 ? 2 : 3);
     static constexpr int kWBytes = ACC_COLS * 64 * 2;
@@ -521,7 +578,7 @@ template <int ACC_COLS> struct VhCfg {
 };
 
 template <int ACC_COLS>
-__global__ void __launch_bounds__(VC_THREADS, VhCfg<ACC_COLS>::kMinBlocks)
+__global__ void __launch_bounds__(VhCfg<ACC_COLS>::kThreads, VhCfg<ACC_COLS>::kMinBlocks)
 voc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX /* box 64 x a_rows x 1 */, const __grid_constant__ CUtensorMap tmW, VocConvParams p,
                      int a_rows) {
     using Cfg = VhCfg<ACC_COLS>;
@@ -546,7 +603,7 @@ voc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX /* box 64 x a_rows 
     if (warp_idx == 1 && lane == 0) {
         for (int s = 0; s < VH_A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < Cfg::kWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4 * Cfg::kEpiSets); }
         fence_barrier_init();
     }
     if (warp_idx == 2) tmem_alloc<2 * ACC_COLS>(tmem_slot);
@@ -614,7 +671,7 @@ voc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX /* box 64 x a_rows 
             const int nt = tile % n_tiles, mt = (tile / n_tiles) % m_tiles, b = tile / (n_tiles * m_tiles);
             mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
             tc_fence_after();
-            voc_epilogue_rows(p, tmem_base + acc * ACC_COLS, quad, lane, nt, mt, b, vec);
+            voc_epilogue_rows(p, tmem_base + acc * ACC_COLS, quad, lane, nt, mt, b, vec, (warp_idx - 2) >> 2, Cfg::kEpiSets);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);

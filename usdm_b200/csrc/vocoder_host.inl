@@ -36,6 +36,7 @@ struct tvb_voc_handle {
     float *X = nullptr, *XS = nullptr, *U = nullptr, *R = nullptr, *Hb = nullptr, *AF = nullptr;
     bf16* A16 = nullptr;
     // profiling
+    int opt_act_vec2 = 1;                         // 1 = two channels per thread with packed fp32x2 math in the activation kernel (bf16 path, even C)
     int opt_halo = 1;                             // 1 = halo kernel (activation tile fetched once per tile), 0 = one fetch per tap
     bool profile = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -372,12 +373,16 @@ static int voc_act(tvb_voc_handle* h, const std::string& name, const float* x, i
     if (it == h->acts.end()) return fail(TVB_ERR_STATE, "no activation %s", name.c_str());
     const VocActW& a = it->second;
     const int chunks = (T + VOC_ACT_TT - 1) / VOC_ACT_TT;
-    dim3 block(128), grid(static_cast<unsigned>((static_cast<long long>(chunks) * a.C + 127) / 128), B);
+    const bool tc = h->precision == TVB_PRECISION_BF16 && !force_f32;
+    const int vec = (tc && h->opt_act_vec2 && (a.C & 1) == 0) ? 2 : 1;
+    dim3 block(128), grid(static_cast<unsigned>((static_cast<long long>(chunks) * (a.C / vec) + 127) / 128), B);
     VocProf ps(h, st, 1);
-    if (h->precision == TVB_PRECISION_BF16 && !force_f32)
-        k_voc_act<bf16, true><<<grid, block, 0, st>>>(x, a.C, T, round_up(a.C, 8), a.consts, a.F, h->A16);
+    if (tc && vec == 2)
+        k_voc_act<bf16, true, 2><<<grid, block, 0, st>>>(x, a.C, T, round_up(a.C, 8), a.consts, a.F, h->A16);
+    else if (tc)
+        k_voc_act<bf16, true, 1><<<grid, block, 0, st>>>(x, a.C, T, round_up(a.C, 8), a.consts, a.F, h->A16);
     else
-        k_voc_act<float, false><<<grid, block, 0, st>>>(x, a.C, T, a.C, a.consts, a.F, h->AF);
+        k_voc_act<float, false, 1><<<grid, block, 0, st>>>(x, a.C, T, a.C, a.consts, a.F, h->AF);
     CKL();
     return TVB_OK;
 }
@@ -396,11 +401,11 @@ static int voc_conv(tvb_voc_handle* h, const VocConv& L, const float* in32, int 
         if (h->opt_halo && a_rows <= VH_A_ROWS) {
             TRY(make_tmap_act3(&tmX, h->A16, L.Cin, round_up(L.Cin, 8), T, B, a_rows));
             if (L.bn > 128)
-                voc_conv_halo_kernel<256><<<std::min(tiles, h->num_sms * VhCfg<256>::kMinBlocks), VC_THREADS, VhCfg<256>::kSmem, st>>>(tmX, L.tmW, p, a_rows);
+                voc_conv_halo_kernel<256><<<std::min(tiles, h->num_sms * VhCfg<256>::kMinBlocks), VhCfg<256>::kThreads, VhCfg<256>::kSmem, st>>>(tmX, L.tmW, p, a_rows);
             else if (L.bn > 64)
-                voc_conv_halo_kernel<128><<<std::min(tiles, h->num_sms * VhCfg<128>::kMinBlocks), VC_THREADS, VhCfg<128>::kSmem, st>>>(tmX, L.tmW, p, a_rows);
+                voc_conv_halo_kernel<128><<<std::min(tiles, h->num_sms * VhCfg<128>::kMinBlocks), VhCfg<128>::kThreads, VhCfg<128>::kSmem, st>>>(tmX, L.tmW, p, a_rows);
             else
-                voc_conv_halo_kernel<64><<<std::min(tiles, h->num_sms * VhCfg<64>::kMinBlocks), VC_THREADS, VhCfg<64>::kSmem, st>>>(tmX, L.tmW, p, a_rows);
+                voc_conv_halo_kernel<64><<<std::min(tiles, h->num_sms * VhCfg<64>::kMinBlocks), VhCfg<64>::kThreads, VhCfg<64>::kSmem, st>>>(tmX, L.tmW, p, a_rows);
         } else {
             TRY(make_tmap_act3(&tmX, h->A16, L.Cin, round_up(L.Cin, 8), T, B));
             if (L.bn > 128)
@@ -510,6 +515,7 @@ extern "C" int tvb_voc_debug_activation(tvb_voc_handle* h, const char* name, con
 extern "C" int tvb_voc_set_option(tvb_voc_handle* h, const char* name, int32_t value) {
     if (!h || !name) return fail(TVB_ERR_INVALID, "null argument");
     if (!strcmp(name, "halo")) h->opt_halo = value;
+    else if (!strcmp(name, "act_vec2")) h->opt_act_vec2 = value;
     else return fail(TVB_ERR_INVALID, "unknown vocoder option %s", name);
     return TVB_OK;
 }
