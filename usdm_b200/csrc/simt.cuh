@@ -111,6 +111,62 @@ k_frame_proj(RowLayout L, int T, int nf, int H, const float* __restrict__ Wt, co
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// bf16-path prologue of every estimator pass (replaces k_frame_proj<false> when the tensor-core frame projection is on):
+// gathers the ODE state y [B][nf][T] (networks.py:302-309) into the packed-row GEMM operand
+//     A[row][0:nf] = hi(y),  A[row][nf:2nf] = lo(y)   (y = hi + lo to 2^-17 in two bf16 planes),  zero elsewhere,
+// so that A . [W_y | W_y | 0]^T + base is the frame projection on the tensor core, and writes this pass's time-token rows
+// (raw sinusoid of 1000 t, networks.py:22-26) into `base`, the GEMM's residual operand.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int PY_ROWS = 32;
+__global__ void __launch_bounds__(256)
+k_pack_y(RowLayout L, int T, int nf, int H, int ldA, const float* __restrict__ y, const float* __restrict__ t_seq, float t_uniform,
+         const float* __restrict__ freqs, float* __restrict__ base, __nv_bfloat16* __restrict__ A) {
+    extern __shared__ float s_y[];       // [PY_ROWS][nf + 1]
+    __shared__ int s_seq[PY_ROWS], s_pos[PY_ROWS];
+    const int r0 = blockIdx.x * PY_ROWS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < PY_ROWS) {
+        s_seq[threadIdx.x] = L.row_seq[r0 + threadIdx.x];
+        s_pos[threadIdx.x] = L.row_pos[r0 + threadIdx.x];
+    }
+    __syncthreads();
+    {   // lane = row: consecutive rows are consecutive frames of one utterance, so each channel's read is contiguous
+        const int seq = s_seq[lane], pos = s_pos[lane];
+        const bool live = seq >= 0 && pos >= 1;
+        const float* src = live ? y + static_cast<size_t>(L.seq_utt[seq]) * nf * T + (pos - 1) : y;
+        for (int c = warp; c < nf; c += 8) s_y[lane * (nf + 1) + c] = live ? __ldg(src + static_cast<size_t>(c) * T) : 0.f;
+    }
+    __syncthreads();
+    const int pairs = ldA / 2;
+    for (int idx = threadIdx.x; idx < PY_ROWS * pairs; idx += blockDim.x) {
+        const int r = idx / pairs, k = (idx - r * pairs) * 2;
+        float v[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int kk = k + j;
+            if (kk < nf) v[j] = __bfloat162float(__float2bfloat16(s_y[r * (nf + 1) + kk]));
+            else if (kk < 2 * nf) { const float f = s_y[r * (nf + 1) + kk - nf]; v[j] = f - __bfloat162float(__float2bfloat16(f)); }
+            else v[j] = 0.f;
+        }
+        *reinterpret_cast<uint32_t*>(A + static_cast<size_t>(r0 + r) * ldA + k) = pack_bf16x2(v[0], v[1]);
+    }
+    for (int r = 0; r < PY_ROWS; ++r) {
+        if (s_seq[r] < 0 || s_pos[r] != 0) continue;             // block-uniform
+        const float st = 1000.0f * (t_seq ? t_seq[s_seq[r]] : t_uniform);      // (scale * x) * emb, networks.py:26
+        const int half = H / 2;
+        for (int n = threadIdx.x; n < H; n += blockDim.x)
+            base[static_cast<size_t>(r0 + r) * H + n] = (n < half) ? sinf(st * freqs[n]) : cosf(st * freqs[n - half]);
+    }
+}
+// W2[n][k] = W_y[n][k] for k < nf, W_y[n][k - nf] for k < 2 nf, 0 up to ld   (Wy_t is W_y transposed: [nf][H])
+__global__ void k_build_wy2(const float* __restrict__ Wy_t, int nf, int H, int ld, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H * ld) return;
+    const int n = i / ld, k = i % ld;
+    out[i] = k < nf ? Wy_t[static_cast<size_t>(k) * H + n] : (k < 2 * nf ? Wy_t[static_cast<size_t>(k - nf) * H + n] : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // LayerNorm over the hidden dim (eps 1e-5; networks.py:348, :259, :263) + the row mask that follows it.
 // One warp per row, the row held in registers (H <= 1024, H % 128 == 0), two-pass mean / variance in fp32.
 // Writes the fp32 residual stream and, on the bf16 path, the bf16 copy the next GEMM consumes through TMA.

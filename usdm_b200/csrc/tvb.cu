@@ -140,6 +140,7 @@ struct tvb_handle {
     int opt_gemm_2cta = 1;      // bf16 path: 1 = CTA-pair (cta_group::2) GEMM, 0 = single-CTA GEMM
     int opt_ln1_fold = 1;       // bf16 path with ln_fuse == 1: LN1 folded into the FFN-in GEMM (no LN1 kernel, attention-out epilogue emits
                                 // a bf16 copy + row statistics); 0 = LN1 as a kernel
+    int opt_frame_tc = 1;       // bf16 path: 1 = per-pass frame projection (y -> hidden) as a tcgen05 GEMM over a hi/lo bf16 split of y, 0 = CUDA-core kernel
     int opt_pdl = 1;            // 1 = GEMM / attention / LayerNorm kernels are launched with programmatic stream serialization: their set-up
                                 // overlaps the tail of the previous kernel (griddepcontrol), 0 = ordinary launches
     int opt_graph = 1;          // 1 = small batches (<= 16384 packed rows) replay one estimator pass as a CUDA graph inside tvb_solve
@@ -199,6 +200,10 @@ struct tvb_handle {
     float2 *statsA = nullptr, *statsB = nullptr;       // per-row (mean, rstd) of the two LayerNorms in flight (ln_fuse)
     float2* ln_part = nullptr;                         // [Mp, 8] partial row statistics (ln1_fold)
     float *z_work = nullptr, *z_hat = nullptr, *v_pred = nullptr;
+    CUtensorMap tm_base, tm_hin32;               // fp32 maps of `base` (residual of the frame-projection GEMM) and of hin.f32 (its output)
+    Lin lin_y;                                   // frame projection of the ODE state: [H, KY] = [W_y | W_y | 0] in bf16 (KY = 2 n_feats rounded up to 64)
+    Act yop;                                     // its A operand: hi / lo bf16 planes of y in packed rows
+    float *wy2 = nullptr, *zero_bias = nullptr;
     CUtensorMap tm_xpre, tm_xalt, tm_hres;       // fp32 [Mp, H] epilogue maps (box 32 rows x 32 columns): TMA store / residual load
 };
 
@@ -396,6 +401,15 @@ extern "C" int tvb_finalize_weights(tvb_handle* h) {
     k_transpose_slice<<<(nf * H + 255) / 256, 256>>>(w_in, ldin, E, nf, H, h->Wy_t);
     k_transpose_slice<<<(nf * H + 255) / 256, 256>>>(w_in, ldin, E + nf, nf, H, h->Wc_t);
     CKL();
+    {   // tensor-core frame projection operand: [W_y | W_y | 0] (the two halves meet the hi and lo bf16 planes of y)
+        const int KY = (2 * nf + 63) / 64 * 64;
+        TRY(dev_alloc_t(h, h->owned, &h->wy2, static_cast<size_t>(H) * KY));
+        TRY(dev_alloc_t(h, h->owned, &h->zero_bias, static_cast<size_t>(H)));
+        CK(cudaMemset(h->zero_bias, 0, sizeof(float) * H));
+        k_build_wy2<<<(H * KY + 255) / 256, 256>>>(h->Wy_t, nf, H, KY, h->wy2);
+        CKL();
+        TRY(make_lin(h, &h->lin_y, h->wy2, h->zero_bias, H, KY));
+    }
     // time-token frequencies f_k = exp(-k ln(1e4)/(H/2-1))                                    (networks.py:22-25)
     {
         std::vector<float> f(H / 2);
@@ -565,6 +579,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     else if (!strcmp(name, "zigzag")) h->opt_zigzag = value ? 1 : 0;
     else if (!strcmp(name, "graph")) h->opt_graph = value ? 1 : 0;
     else if (!strcmp(name, "pdl")) h->opt_pdl = value ? 1 : 0;
+    else if (!strcmp(name, "frame_tc")) h->opt_frame_tc = value ? 1 : 0;
     else if (!strcmp(name, "ln1_fold")) h->opt_ln1_fold = value ? 1 : 0;
     else if (!strcmp(name, "attn_ptmem")) h->opt_attn_ptmem = value ? 1 : 0;
     else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 8) return fail(TVB_ERR_INVALID, "attn_v must be 3 .. 8"); h->opt_attn_v = value; }
@@ -688,6 +703,7 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
             TRY(dev_alloc_t(h, h->ws_owned, &h->hin.b16, static_cast<size_t>(rows) * H));
             CK(cudaMemset(h->hin.b16, 0, static_cast<size_t>(rows) * H * sizeof(bf16)));
         }
+        if (bf) TRY(alloc_act(h, &h->yop, rows, h->lin_y.K, true));
         TRY(alloc_act(h, &h->p1, rows, H, bf));
         for (int i = 0; i < nl / 2; ++i) TRY(alloc_act(h, &h->slots[i], rows, H, bf));
         TRY(alloc_act(h, &h->hbA, rows, H, bf));
@@ -733,6 +749,10 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
         TRY(make_tmap(&h->qkv.tm_out, h->qkv.b16, Mp, 3 * H, 3 * H, 32));
         TRY(make_tmap(&h->mid.tm_out, h->mid.b16, Mp, F, F, 32));
         TRY(make_tmap(&h->hbB.tm_out32, h->hbB.b16, Mp, H, H, 32, 32, false, true));
+        TRY(make_tmap(&h->yop.tm, h->yop.b16, Mp, h->lin_y.K, h->lin_y.K, 128));
+        TRY(make_tmap(&h->hin.tm_out32, h->hin.b16, Mp, H, H, 32, 32, false, true));
+        TRY(make_tmap(&h->tm_base, h->base, Mp, H, H, 32, 32, true));
+        TRY(make_tmap(&h->tm_hin32, h->hin.f32, Mp, H, H, 32, 32, true));
         TRY(make_tmap(&h->tm_xpre, h->xpre, Mp, H, H, 32, 32, true));
         TRY(make_tmap(&h->tm_hres, h->hres, Mp, H, H, 32, 32, true));
         TRY(make_tmap(&h->tm_xalt, h->xalt, Mp, H, H, 32, 32, true));
@@ -895,7 +915,7 @@ struct LnRef {
     const float *g = nullptr, *b = nullptr;
 };
 static const CUtensorMap& f32_map(tvb_handle* h, const float* ptr) {
-    return ptr == h->xpre ? h->tm_xpre : ptr == h->xalt ? h->tm_xalt : h->tm_hres;
+    return ptr == h->xpre ? h->tm_xpre : ptr == h->xalt ? h->tm_xalt : ptr == h->base ? h->tm_base : ptr == h->hin.f32 ? h->tm_hin32 : h->tm_hres;
 }
 // y = [a | a2] W^T + b with the epilogue the call site needs, in the active precision.
 //   LE_PLAIN: -> out (Act)          LE_GELU: -> gelu -> out (Act)
@@ -1052,13 +1072,24 @@ static int run_estimator(tvb_handle* h, const float* y, const float* t_seq_dev, 
     const int Mp = h->L.Mp, H = c.hidden_size, nl = c.num_hidden_layers, nf = c.n_feats;
     const bool bf = h->precision == TVB_PRECISION_BF16;
     const size_t smem = static_cast<size_t>(nf) * FP_ROWS * sizeof(float);
-    {
+    if (bf && h->opt_frame_tc && h->opt_gemm_2cta && !h->opt_gemm_mc && H % 256 == 0) {
+        // hin = [hi(y) | lo(y)] . [W_y | W_y]^T + base on the tensor core (the CUDA-core kernel below needs 3 GFMA per pass, ~110 us
+        // of FMA pipe at best); the epilogue emits the fp32 stream and the bf16 operand copy like the attention-out GEMM does
+        {
+            ProfScope ps(h, st, PC_FRAME);
+            k_pack_y<<<Mp / PY_ROWS, 256, static_cast<size_t>(PY_ROWS) * (nf + 1) * sizeof(float), st>>>(
+                h->L, h->plan_T, nf, H, h->lin_y.K, y, t_seq_dev, t_uniform, h->freqs, h->base, h->yop.b16);
+            h->launches++;
+            CKL();
+        }
+        TRY(linear(h, h->lin_y, h->yop, nullptr, LE_RESID_ST, &h->hin, h->base, h->hin.f32, st, PC_FRAME));
+    } else {
         ProfScope ps(h, st, PC_FRAME);
         k_frame_proj<false><<<Mp / FP_ROWS, 256, smem, st>>>(h->L, h->plan_T, nf, H, h->Wy_t, y, nullptr, nullptr, nullptr, 0, 0, h->base,
                                                              t_seq_dev, t_uniform, h->freqs, h->hin.f32, bf ? h->hin.b16 : nullptr);
+        h->launches++;
+        CKL();
     }
-    h->launches++;
-    CKL();
     for (int i = 0; i < c.convpos_depth; ++i) TRY(posconv(h, i, i == c.convpos_depth - 1, st));
     // ln_fuse (bf16 path): the fp32 post-LN stream is never written.  Each LayerNorm emits the bf16 GEMM operand and per-row
     // (mean, rstd); the residual GEMM that needs LayerNorm(x) in fp32 re-normalises x in its epilogue.  The pre-norm sums
