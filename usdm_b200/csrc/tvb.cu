@@ -140,6 +140,7 @@ struct tvb_handle {
     int opt_gemm_2cta = 1;      // bf16 path: 1 = CTA-pair (cta_group::2) GEMM, 0 = single-CTA GEMM
     int opt_ln1_fold = 1;       // bf16 path with ln_fuse == 1: LN1 folded into the FFN-in GEMM (no LN1 kernel, attention-out epilogue emits
                                 // a bf16 copy + row statistics); 0 = LN1 as a kernel
+    int opt_out_tc = 1;         // bf16 path: 1 = output projection (hidden -> n_feats) as a tcgen05 GEMM on the last LayerNorm's bf16 output, 0 = fp32 CUDA-core GEMM
     int opt_frame_tc = 1;       // bf16 path: 1 = per-pass frame projection (y -> hidden) as a tcgen05 GEMM over a hi/lo bf16 split of y, 0 = CUDA-core kernel
     int opt_pdl = 1;            // 1 = GEMM / attention / LayerNorm kernels are launched with programmatic stream serialization: their set-up
                                 // overlaps the tail of the previous kernel (griddepcontrol), 0 = ordinary launches
@@ -201,6 +202,10 @@ struct tvb_handle {
     float2* ln_part = nullptr;                         // [Mp, 8] partial row statistics (ln1_fold)
     float *z_work = nullptr, *z_hat = nullptr, *v_pred = nullptr;
     CUtensorMap tm_base, tm_hin32;               // fp32 maps of `base` (residual of the frame-projection GEMM) and of hin.f32 (its output)
+    Lin lin_out;                                 // output projection padded to one 256-column tile: [256, H] (rows >= n_feats are zero)
+    float *wout2 = nullptr, *bout2 = nullptr;
+    int vbuf_ld = 0;                             // row stride of vbuf as written by the last estimator pass (n_feats, or 256 on the tensor-core path)
+    CUtensorMap tm_vbuf;
     Lin lin_y;                                   // frame projection of the ODE state: [H, KY] = [W_y | W_y | 0] in bf16 (KY = 2 n_feats rounded up to 64)
     Act yop;                                     // its A operand: hi / lo bf16 planes of y in packed rows
     float *wy2 = nullptr, *zero_bias = nullptr;
@@ -533,6 +538,15 @@ extern "C" int tvb_finalize_weights(tvb_handle* h) {
     }
     TRY(need(h, p + "proj_out.weight", {nf, H, 1}, &h->w_out));
     TRY(need(h, p + "proj_out.bias", {nf}, &h->b_out));
+    if (nf <= 256) {   // tensor-core output projection operand
+        TRY(dev_alloc_t(h, h->owned, &h->wout2, static_cast<size_t>(256) * H));
+        TRY(dev_alloc_t(h, h->owned, &h->bout2, static_cast<size_t>(256)));
+        CK(cudaMemset(h->wout2, 0, sizeof(float) * 256 * H));
+        CK(cudaMemset(h->bout2, 0, sizeof(float) * 256));
+        CK(cudaMemcpy(h->wout2, h->w_out, sizeof(float) * nf * H, cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(h->bout2, h->b_out, sizeof(float) * nf, cudaMemcpyDeviceToDevice));
+        TRY(make_lin(h, &h->lin_out, h->wout2, h->bout2, 256, H));
+    }
     CK(cudaDeviceSynchronize());
     cudaFree(wqkv_tc);
     h->finalized = true;
@@ -580,6 +594,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     else if (!strcmp(name, "graph")) h->opt_graph = value ? 1 : 0;
     else if (!strcmp(name, "pdl")) h->opt_pdl = value ? 1 : 0;
     else if (!strcmp(name, "frame_tc")) h->opt_frame_tc = value ? 1 : 0;
+    else if (!strcmp(name, "out_tc")) h->opt_out_tc = value ? 1 : 0;
     else if (!strcmp(name, "ln1_fold")) h->opt_ln1_fold = value ? 1 : 0;
     else if (!strcmp(name, "attn_ptmem")) h->opt_attn_ptmem = value ? 1 : 0;
     else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 8) return fail(TVB_ERR_INVALID, "attn_v must be 3 .. 8"); h->opt_attn_v = value; }
@@ -694,7 +709,7 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
         TRY(alloc_f32(h, reinterpret_cast<float**>(&h->statsB), 2 * static_cast<size_t>(rows)));
         TRY(alloc_f32(h, reinterpret_cast<float**>(&h->ln_part), 16 * static_cast<size_t>(rows)));
         TRY(alloc_f32(h, &h->hres, static_cast<size_t>(rows) * H));
-        TRY(alloc_f32(h, &h->vbuf, static_cast<size_t>(rows) * nf));
+        TRY(alloc_f32(h, &h->vbuf, static_cast<size_t>(rows) * std::max(nf, 256)));
         TRY(alloc_f32(h, &h->z_work, sn));
         TRY(alloc_f32(h, &h->z_hat, sn));
         TRY(alloc_f32(h, &h->v_pred, sn));
@@ -752,6 +767,7 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
         TRY(make_tmap(&h->yop.tm, h->yop.b16, Mp, h->lin_y.K, h->lin_y.K, 128));
         TRY(make_tmap(&h->hin.tm_out32, h->hin.b16, Mp, H, H, 32, 32, false, true));
         TRY(make_tmap(&h->tm_base, h->base, Mp, H, H, 32, 32, true));
+        TRY(make_tmap(&h->tm_vbuf, h->vbuf, Mp, 256, 256, 32, 32, true));
         TRY(make_tmap(&h->tm_hin32, h->hin.f32, Mp, H, H, 32, 32, true));
         TRY(make_tmap(&h->tm_xpre, h->xpre, Mp, H, H, 32, 32, true));
         TRY(make_tmap(&h->tm_hres, h->hres, Mp, H, H, 32, 32, true));
@@ -907,7 +923,7 @@ static int linear_ln(tvb_handle* h, const Lin& lin, const Act& a, const float* r
     return TVB_OK;
 }
 
-enum LinEpi { LE_PLAIN, LE_GELU, LE_RESID, LE_DUAL, LE_RESID_ST /* + bf16 copy + row statistics */, LE_FOLD_GELU /* LN folded in */ };
+enum LinEpi { LE_PLAIN, LE_GELU, LE_RESID, LE_DUAL, LE_RESID_ST /* + bf16 copy + row statistics */, LE_FOLD_GELU /* LN folded in */, LE_F32 /* fp32 out, no residual */ };
 // LayerNorm whose fp32 result is not materialised: rows of `x` with per-row (mean, rstd) in `stats` and the norm's affine.
 struct LnRef {
     const float* x = nullptr;
@@ -915,7 +931,7 @@ struct LnRef {
     const float *g = nullptr, *b = nullptr;
 };
 static const CUtensorMap& f32_map(tvb_handle* h, const float* ptr) {
-    return ptr == h->xpre ? h->tm_xpre : ptr == h->xalt ? h->tm_xalt : ptr == h->base ? h->tm_base : ptr == h->hin.f32 ? h->tm_hin32 : h->tm_hres;
+    return ptr == h->xpre ? h->tm_xpre : ptr == h->xalt ? h->tm_xalt : ptr == h->base ? h->tm_base : ptr == h->hin.f32 ? h->tm_hin32 : ptr == h->vbuf ? h->tm_vbuf : h->tm_hres;
 }
 // y = [a | a2] W^T + b with the epilogue the call site needs, in the active precision.
 //   LE_PLAIN: -> out (Act)          LE_GELU: -> gelu -> out (Act)
@@ -931,7 +947,7 @@ static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, Li
         if (ln) { p.ln_stats = ln->stats; p.ln_g = ln->g; p.ln_b = ln->b; }
         p.reverse = (rev && h->opt_zigzag) ? 1 : 0;
         const int e = epi == LE_PLAIN ? EPI_BF16 : epi == LE_GELU ? EPI_GELU_BF16 : epi == LE_RESID ? (ln ? EPI_RESID_LN : EPI_RESID_F32)
-                    : epi == LE_RESID_ST ? (ln ? EPI_RESID_LN_ST : EPI_RESID_F32_ST) : epi == LE_FOLD_GELU ? EPI_FOLD_GELU : EPI_DUAL;
+                    : epi == LE_RESID_ST ? (ln ? EPI_RESID_LN_ST : EPI_RESID_F32_ST) : epi == LE_FOLD_GELU ? EPI_FOLD_GELU : epi == LE_F32 ? EPI_F32 : EPI_DUAL;
         if (epi == LE_RESID_ST) p.part = h->ln_part;
         if (epi == LE_FOLD_GELU) { p.part = h->ln_part; p.stats_out = h->statsB; p.fold_c = lin.fold_c; }
         if ((epi == LE_RESID_ST || epi == LE_FOLD_GELU) && !(h->opt_gemm_2cta && !h->opt_gemm_mc && lin.N % 256 == 0))
@@ -1096,6 +1112,7 @@ static int run_estimator(tvb_handle* h, const float* y, const float* t_seq_dev, 
     // ping-pong between xpre and xalt: O-proj reads xpre / writes xalt, FFN-out reads xalt / writes xpre.
     const bool epi_ln = bf && h->opt_ln_fuse == 2 && h->opt_gemm_2cta && H == GL_N;   // LayerNorm inside the residual GEMM epilogue
     const bool fuse = bf && h->opt_ln_fuse && !epi_ln;
+    const bool out_tc = fuse && h->opt_out_tc && h->opt_gemm_2cta && !h->opt_gemm_mc && h->lin_out.N == 256;
     LnRef cur_ln;                      // LayerNorm that produced the current layer input (valid when fuse && !plain_resid)
     bool plain_resid = !fuse;          // the current layer input exists as fp32 rows in hres
     // LN1 folded into the FFN-in GEMM (no LN1 kernel): needs the CTA-pair GEMM epilogues
@@ -1149,7 +1166,7 @@ static int run_estimator(tvb_handle* h, const float* y, const float* t_seq_dev, 
             TRY(linear(h, lw.f2, h->mid, nullptr, LE_RESID, nullptr, nullptr, h->xpre, st, PC_GEMM_F2, &ln1, f2_rev));
             Act* dst = (l < nl / 2 - 1) ? &h->slots[sp++] : &h->hbA;
             // the last layer's output feeds the fp32 output projection: materialise it
-            TRY(layernorm(h, h->xpre, last ? h->hres : nullptr, dst, lw.ln2_g, lw.ln2_b, st, h->statsA, ln2_rev));
+            TRY(layernorm(h, h->xpre, (last && !out_tc) ? h->hres : nullptr, dst, lw.ln2_g, lw.ln2_b, st, h->statsA, ln2_rev));
             cur_ln.x = h->xpre; cur_ln.stats = h->statsA; cur_ln.g = lw.ln2_g; cur_ln.b = lw.ln2_b;
             plain_resid = false;
             cur = dst;
@@ -1163,6 +1180,13 @@ static int run_estimator(tvb_handle* h, const float* y, const float* t_seq_dev, 
             cur = dst;
         }
     }
+    if (out_tc) {
+        // output projection H -> n_feats on the tensor core: A = the last LayerNorm's bf16 output, one 256-column tile (n_feats
+        // live columns), fp32 result with row stride 256
+        h->vbuf_ld = 256;
+        return linear(h, h->lin_out, *cur, nullptr, LE_F32, nullptr, nullptr, h->vbuf, st, PC_OUT);
+    }
+    h->vbuf_ld = nf;
     // output projection H -> n_feats on the fp32 residual stream (networks.py:372)
     SgemmParams p{};
     p.M = Mp; p.N = nf; p.K = H; p.K1 = H;
@@ -1226,7 +1250,7 @@ extern "C" int tvb_estimator_forward(tvb_handle* h, const int64_t* x_dev, const 
     TRY(prep_base(h, x_dev, cond_dev, 0, st));
     TRY(run_estimator(h, y_dev, h->d_tseq, 0.f, st));
     const size_t n = static_cast<size_t>(B) * h->cfg.n_feats * T;
-    k_scatter_velocity<<<grid_for(n), 256, 0, st>>>(h->vbuf, h->cfg.n_feats, h->L, h->cfg.n_feats, T, out_v_dev);
+    k_scatter_velocity<<<grid_for(n), 256, 0, st>>>(h->vbuf, h->vbuf_ld, h->L, h->cfg.n_feats, T, out_v_dev);
     h->launches++;
     CKL();
     return TVB_OK;
@@ -1235,7 +1259,7 @@ extern "C" int tvb_estimator_forward(tvb_handle* h, const int64_t* x_dev, const 
 static int ode_update(tvb_handle* h, const OdeParams& p, cudaStream_t st) {
     const size_t n = static_cast<size_t>(p.B) * p.nf * p.T;
     ProfScope ps(h, st, PC_OUT);
-    k_ode_update<<<grid_for(n), 256, 0, st>>>(h->vbuf, h->cfg.n_feats, h->L, p);
+    k_ode_update<<<grid_for(n), 256, 0, st>>>(h->vbuf, h->vbuf_ld, h->L, p);
     h->launches++;
     CKL();
     return TVB_OK;
