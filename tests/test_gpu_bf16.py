@@ -23,6 +23,7 @@ ABLATIONS = [
     dict(attn_tc=0, conv_tc=0, gemm_2cta=0, ln_fuse=1),      # fused-LayerNorm residual epilogue of the single-CTA GEMM
     dict(attn_tc=0, conv_tc=0, gemm_2cta=1, gemm_mc=0, ln_fuse=1),      # ... of the CTA-pair GEMM
     dict(attn_tc=0, conv_tc=0, gemm_mc=1, ln_fuse=1),        # ... of the cluster-of-4 multicast GEMM
+    dict(conv_halo=0),                                       # positional conv with one activation fetch per tap
     dict(out_tc=0),                                          # fp32 CUDA-core output projection (the shipping path is a tcgen05 GEMM on the last LayerNorm's bf16 output)
     dict(frame_tc=0, out_tc=0),
     dict(frame_tc=0),                                        # CUDA-core frame projection (the shipping path is a tcgen05 GEMM over hi/lo bf16 planes of y)

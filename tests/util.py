@@ -51,6 +51,7 @@ def model(seed=0, perturb=False, precision="bf16"):
     m.set_option("pdl", 1)
     m.set_option("frame_tc", 1)
     m.set_option("out_tc", 1)
+    m.set_option("conv_halo", 1)
     return m
 
 

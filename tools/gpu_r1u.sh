@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_bf16.py tests/test_gpu_solve.py tests/test_gpu_configs.py tests/test_gpu_fp32.py -q -m gpu -x -s > gpurun_out/t_frame.log 2>&1; echo "pytest exit $?" > gpurun_out/summary.txt
 i=0
-for cfg in "out_tc=1" "out_tc=0" "out_tc=1" "out_tc=0"; do
+for cfg in "conv_halo=1" "conv_halo=0" "conv_halo=1" "conv_halo=0"; do
   timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-vocoder --opt $cfg > "gpurun_out/bench_u$i.json" 2> "gpurun_out/bench_u$i.err"; echo "bench u$i [$cfg] exit $?" >> gpurun_out/summary.txt
   i=$((i+1))
 done

@@ -140,6 +140,7 @@ struct tvb_handle {
     int opt_gemm_2cta = 1;      // bf16 path: 1 = CTA-pair (cta_group::2) GEMM, 0 = single-CTA GEMM
     int opt_ln1_fold = 1;       // bf16 path with ln_fuse == 1: LN1 folded into the FFN-in GEMM (no LN1 kernel, attention-out epilogue emits
                                 // a bf16 copy + row statistics); 0 = LN1 as a kernel
+    int opt_conv_halo = 1;      // tcgen05 positional conv: 1 = halo kernel (activation tile fetched once per 256-row tile, taps as row-shifted descriptors), 0 = one fetch per tap
     int opt_out_tc = 1;         // bf16 path: 1 = output projection (hidden -> n_feats) as a tcgen05 GEMM on the last LayerNorm's bf16 output, 0 = fp32 CUDA-core GEMM
     int opt_frame_tc = 1;       // bf16 path: 1 = per-pass frame projection (y -> hidden) as a tcgen05 GEMM over a hi/lo bf16 split of y, 0 = CUDA-core kernel
     int opt_pdl = 1;            // 1 = GEMM / attention / LayerNorm kernels are launched with programmatic stream serialization: their set-up
@@ -201,6 +202,7 @@ struct tvb_handle {
     float2 *statsA = nullptr, *statsB = nullptr;       // per-row (mean, rstd) of the two LayerNorms in flight (ln_fuse)
     float2* ln_part = nullptr;                         // [Mp, 8] partial row statistics (ln1_fold)
     float *z_work = nullptr, *z_hat = nullptr, *v_pred = nullptr;
+    CUtensorMap tm_hin_halo, tm_p1_halo;         // positional-conv A operand maps with the halo (box 160 rows x 64 columns)
     CUtensorMap tm_base, tm_hin32;               // fp32 maps of `base` (residual of the frame-projection GEMM) and of hin.f32 (its output)
     Lin lin_out;                                 // output projection padded to one 256-column tile: [256, H] (rows >= n_feats are zero)
     float *wout2 = nullptr, *bout2 = nullptr;
@@ -595,6 +597,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     else if (!strcmp(name, "pdl")) h->opt_pdl = value ? 1 : 0;
     else if (!strcmp(name, "frame_tc")) h->opt_frame_tc = value ? 1 : 0;
     else if (!strcmp(name, "out_tc")) h->opt_out_tc = value ? 1 : 0;
+    else if (!strcmp(name, "conv_halo")) h->opt_conv_halo = value ? 1 : 0;
     else if (!strcmp(name, "ln1_fold")) h->opt_ln1_fold = value ? 1 : 0;
     else if (!strcmp(name, "attn_ptmem")) h->opt_attn_ptmem = value ? 1 : 0;
     else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 8) return fail(TVB_ERR_INVALID, "attn_v must be 3 .. 8"); h->opt_attn_v = value; }
@@ -765,6 +768,8 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
         TRY(make_tmap(&h->mid.tm_out, h->mid.b16, Mp, F, F, 32));
         TRY(make_tmap(&h->hbB.tm_out32, h->hbB.b16, Mp, H, H, 32, 32, false, true));
         TRY(make_tmap(&h->yop.tm, h->yop.b16, Mp, h->lin_y.K, h->lin_y.K, 128));
+        TRY(make_tmap(&h->tm_hin_halo, h->hin.b16, Mp, H, H, CH_ROWS));
+        TRY(make_tmap(&h->tm_p1_halo, h->p1.b16, Mp, H, H, CH_ROWS));
         TRY(make_tmap(&h->hin.tm_out32, h->hin.b16, Mp, H, H, 32, 32, false, true));
         TRY(make_tmap(&h->tm_base, h->base, Mp, H, H, 32, 32, true));
         TRY(make_tmap(&h->tm_vbuf, h->vbuf, Mp, 256, 256, 32, 32, true));
@@ -1041,6 +1046,12 @@ static int posconv(tvb_handle* h, int i, bool last, cudaStream_t st) {
     ProfScope ps(h, st, PC_CONV);
     if (bf && h->opt_conv_tc) {
         // in: hin (first) or p1; out: p1 bf16 (not last) or xpre fp32 = gelu*mask + hin (last)
+        if (h->opt_conv_halo && Mp % 256 == 0 && taps / 2 <= (CH_ROWS - 128) / 2 && H == c.convpos_groups * 64) {
+            CK(launch_conv_halo_raw(first ? h->tm_hin_halo : h->tm_p1_halo, h->conv_tm[i], h->conv_bias[i], h->L.row_seq, Mp, H, taps, c.convpos_groups,
+                                    last ? nullptr : h->p1.b16, last ? h->xpre : nullptr, last ? h->hin.f32 : nullptr, h->num_sms, st));
+            h->launches++;
+            return TVB_OK;
+        }
         const CUtensorMap& tin = first ? h->hin.tm : h->p1.tm;
         CK(launch_conv_tc_raw(tin, h->conv_tm[i], h->conv_bias[i], h->L.row_seq, Mp, H, taps, c.convpos_groups,
                               last ? nullptr : h->p1.b16, last ? h->xpre : nullptr, last ? h->hin.f32 : nullptr, h->num_sms, st));
