@@ -272,7 +272,9 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                         const uint64_t off2 = pack2f(off, off);
                         uint64_t acc2 = pack2f(0.f, 0.f), accp2 = pack2f(0.f, 0.f);
                         float pace_a = 0.f, pace_b = 0.f;
+#ifdef ATT8_MAX_GUARD
                         float mxa = -INFINITY, mxb = -INFINITY;
+#endif
                         auto proc = [&](uint32_t(&cur)[32], const int c) {
                             if (diag) {
                                 const float s0raw = __uint_as_float(cur[0]);
@@ -295,8 +297,10 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
 #pragma unroll
                             for (int u = 0; u < 16; ++u) {
                                 const float x0 = __uint_as_float(cur[2 * u]), x1 = __uint_as_float(cur[2 * u + 1]);
+#ifdef ATT8_MAX_GUARD
                                 if (u & 1) mxb = fmaxf(mxb, fmaxf(x0, x1));
                                 else mxa = fmaxf(mxa, fmaxf(x0, x1));
+#endif
                                 const uint64_t x2 = fadd2(pack2f(x0, x1), off2);
                                 uint64_t p2;
                                 if (POLY > 0 && (u % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) {
@@ -339,9 +343,17 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                         float a0, a1;
                         unpack2f(fadd2(acc2, accp2), a0, a1);
                         lsum = a0 + a1;
+                        // P must stay <= 2^16: if any row of the warp outgrew its reference, redo the block the careful way (the scores are
+                        // still in TMEM: P is stored only after this check).
+#ifdef ATT8_MAX_GUARD
                         const float m_blk = fmaxf(mxa, mxb) + c_row;          // block maximum in the true (biased) domain
-                        // P must stay <= 2^16: if any row of the warp outgrew its reference, redo the block the careful way
                         need_full = __any_sync(0xffffffffu, m_blk > m_ref + A4_RESCALE_LOG2);
+#else
+                        // The row sum of the block is the guard: every p is >= 0, so sum < 2^16 implies max p < 2^16, and an overflowed
+                        // exponential (inf / NaN) fails the comparison too.  This drops the running maximum (one FMNMX3 per pair of
+                        // scores) from the fast path; a false alarm only costs the careful path, which then keeps the reference.
+                        need_full = __any_sync(0xffffffffu, !(lsum < 65536.0f));
+#endif
                     }
                     bool pv_seen = false;
                     if (need_full) {
