@@ -79,7 +79,9 @@ int tvb_get_precision(const tvb_handle* h);
  * 0 = it runs as a kernel), "zigzag" (1 = producer / consumer kernels walk the rows in opposite directions for L2 reuse,
  * default), "graph" (1 = tvb_solve replays the estimator pass of small batches as a CUDA graph, default; 0 = direct launches),
  * "pdl" (1 = GEMM / attention / LayerNorm kernels use programmatic dependent launch, default), "attn_pace" (attention v8 MUFU
- * pacing ablation, default 0), and "profile" (see tvb_profile_read). */
+ * pacing ablation, default 0), "frame_tc" / "out_tc" (1 = the per-pass frame projection of the ODE state / the output
+ * projection run as tcgen05 GEMMs, default; 0 = the CUDA-core kernels), "conv_halo" (1 = positional conv fetches each
+ * activation tile once with its halo, default; 0 = one fetch per tap), and "profile" (see tvb_profile_read). */
 int tvb_set_option(tvb_handle* h, const char* name, int32_t value);
 
 /* Replaces: Transformer.forward(x, y, cond, t, lengths) (networks.py:302-374) — the per-step velocity estimator.
