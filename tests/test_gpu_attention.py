@@ -35,7 +35,7 @@ def _reference(qkv, starts, lens, slopes):
     return out
 
 
-def _run(lens, version, poly, seed=0, scale=1.0):
+def _run(lens, version, poly, seed=0, scale=1.0, spikes=()):
     from usdm_b200 import engine
     lib = engine.load_library()
     g = torch.Generator(device="cuda").manual_seed(seed)
@@ -46,6 +46,10 @@ def _run(lens, version, poly, seed=0, scale=1.0):
     rows = (o + 255) // 256 * 256
     qkv = torch.randn(rows, 3 * H, device="cuda", generator=g) * scale
     qkv[:, :H] *= 0.125 * LOG2E
+    for seq, j, height in spikes:       # one key whose score towers `height` (log2 units) above the rest for every query of the sequence
+        st, L = starts[seq], lens[seq]
+        qkv[st:st + L, :H] += 1.0 / 8.0                               # + e per head, |e| = 1 over the 64 head dims
+        qkv[st + j, H:2 * H] += height / 8.0                          # + height * e  ->  q.k gains ~height
     qkv = qkv.to(torch.bfloat16)
     ctx = torch.zeros(rows, H, device="cuda", dtype=torch.bfloat16)
     slopes = _slopes().cuda()
@@ -80,6 +84,20 @@ def test_attention_peaky_scores_exercise_rescale(version, poly):
     """Large-magnitude q.k (std ~ 40 in the log2 domain) so that block maxima jump by more than 2^16 and the lazy O rescale runs."""
     rel, mx = _run([1134, 640, 300], version, poly, seed=1, scale=3.0)
     print(f"attention v{version} poly={poly}, peaky: rel-L2 {rel:.3e}, max-abs {mx:.3e}")
+    assert rel < 6e-3
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("poly", [0, 2, 3, 4])
+def test_attention_v8_single_key_spike_beyond_the_polynomial_range(poly):
+    """The fast path's overflow guard: one key 200 log2 units above everything else, sitting in a LATER key block at a column the
+    FMA-pipe polynomial handles (columns 4, 5, 10, 11, ... of each 32-column chunk for poly = 3) and, in other sequences, at a MUFU
+    column and in the first block.  2^200 is beyond both the polynomial's exponent range and fp32; the guard must send the block
+    to the careful path, after which the softmax is one-hot on the spike."""
+    lens = [700, 640, 513, 300]
+    spikes = [(0, 2 * 128 + 4, 200.0), (1, 3 * 128 + 37, 200.0), (2, 1 * 128 + 1, 200.0), (3, 7, 200.0)]
+    rel, mx = _run(lens, 8, poly, seed=5, scale=0.3, spikes=spikes)
+    print(f"attention v8 poly={poly}, single-key spikes: rel-L2 {rel:.3e}, max-abs {mx:.3e}")
     assert rel < 6e-3
 
 

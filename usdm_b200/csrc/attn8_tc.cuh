@@ -274,6 +274,8 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                         float pace_a = 0.f, pace_b = 0.f;
 #ifdef ATT8_MAX_GUARD
                         float mxa = -INFINITY, mxb = -INFINITY;
+#else
+                        float mxp = -INFINITY;               // largest argument handed to the polynomial (see the guard below)
 #endif
                         auto proc = [&](uint32_t(&cur)[32], const int c) {
                             if (diag) {
@@ -304,6 +306,13 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                                 const uint64_t x2 = fadd2(pack2f(x0, x1), off2);
                                 uint64_t p2;
                                 if (POLY > 0 && (u % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) {
+#ifndef ATT8_MAX_GUARD
+                                    {
+                                        float g0, g1;
+                                        unpack2f(x2, g0, g1);
+                                        mxp = fmaxf(mxp, fmaxf(g0, g1));
+                                    }
+#endif
                                     p2 = exp2_poly2(x2);
                                     accp2 = fadd2(accp2, p2);               // polynomial pairs: own accumulator, off the pacing chain
                                 } else {
@@ -350,9 +359,11 @@ attn8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                         need_full = __any_sync(0xffffffffu, m_blk > m_ref + A4_RESCALE_LOG2);
 #else
                         // The row sum of the block is the guard: every p is >= 0, so sum < 2^16 implies max p < 2^16, and an overflowed
-                        // exponential (inf / NaN) fails the comparison too.  This drops the running maximum (one FMNMX3 per pair of
-                        // scores) from the fast path; a false alarm only costs the careful path, which then keeps the reference.
-                        need_full = __any_sync(0xffffffffu, !(lsum < 65536.0f));
+                        // MUFU exponential (inf / NaN) fails the comparison too.  The FMA-pipe polynomial is only valid up to 2^126 and
+                        // would wrap silently beyond, so the pairs it handles (one in POLY) keep a running maximum of their arguments.
+                        // This drops two thirds of the fast path's FMNMX3 (one per pair of scores before); a false alarm only costs
+                        // the careful path, which then keeps the reference.
+                        need_full = __any_sync(0xffffffffu, !(lsum < 65536.0f) || mxp > A4_RESCALE_LOG2);
 #endif
                     }
                     bool pv_seen = false;
