@@ -27,7 +27,7 @@ P = 272
 NFE = 32
 
 
-def batch(lens_target, seed, dev):
+def batch(lens_target, seed, dev, P=P):
     g = torch.Generator().manual_seed(seed)
     lens = [t + P for t in lens_target]
     B, T = len(lens), max(lens)
@@ -53,6 +53,9 @@ def main():
     def gen(x, cond, L):
         return model.generate(x, cond, L, NFE, solver="euler", gradient_scale=1.0, speech_prompt=True, prompt_lengths=plen)
 
+    def gen_noprompt(x, cond, L):
+        return model.generate(x, cond, L, NFE, solver="euler", gradient_scale=1.0, speech_prompt=False)
+
     def timed(fn, reps):
         fn()
         torch.cuda.synchronize()
@@ -76,17 +79,23 @@ def main():
         ("configs[2]: 8 x 30 s long-form", [frames_for_seconds(30.0)] * 8, 2, False),
         ("configs[3]: ragged 64, 2-20 s", [frames_for_seconds(float(s)) for s in d64], 2, False),
         ("configs[4]: 512 ragged utterances, sharded", [frames_for_seconds(float(s)) for s in d512], 1, True),
+        ("configs[1] without the prompt: 16 x 10 s, S = 862 (SURVEY 8d asks for both)", [frames_for_seconds(10.0)] * 16, 3, False),
     ]
+    only = os.environ.get("SWEEP_ONLY")             # substring filter, e.g. SWEEP_ONLY="without the prompt"
     for name, lens_t, reps, sharded in cases:
-        x, cond, L = batch(lens_t, 7, dev)
+        if only and only not in name:
+            continue
+        noprompt = "without the prompt" in name
+        Pc = 0 if noprompt else P
+        x, cond, L = batch(lens_t, 7, dev, Pc)
         if sharded:
             fn = lambda: parallel.generate_sharded(gen, x, cond, L, max_tokens=80000)
-            tokens = [t + P + 1 for t in lens_t] * 2
+            tokens = [t + Pc + 1 for t in lens_t] * 2
             frames = sum(lens_t)
             per_gpu_flops = F.estimator_flops(tokens, MODEL_CFG)["total"] * NFE / world
         else:
-            fn = lambda: gen(x, cond, L)       # every rank runs the same batch (replicas): per-GPU figure
-            tokens = [t + P + 1 for t in lens_t] * 2
+            fn = (lambda: gen_noprompt(x, cond, L)) if noprompt else (lambda: gen(x, cond, L))   # every rank runs the same batch (replicas)
+            tokens = [t + Pc + 1 for t in lens_t] * 2
             frames = sum(lens_t) * world
             per_gpu_flops = F.estimator_flops(tokens, MODEL_CFG)["total"] * NFE
         sec = timed(fn, reps)
