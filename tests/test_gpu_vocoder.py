@@ -36,6 +36,22 @@ def test_matches_reference_golden(name, cfg, precision):
     assert m.kernel_launches() > 0
 
 
+@pytest.mark.parametrize("option", ["halo", "act_vec2"])
+@pytest.mark.parametrize("name,cfg", [("vocoder_small_b2.pt", "small"), ("vocoder_full_t6.pt", "full")])
+def test_ablation_kernels_match_reference_golden(name, cfg, option):
+    """The kernels behind the tvb_voc_set_option switches (one activation fetch per tap instead of the halo tile; the scalar
+    activation kernel instead of the two-channel one) stay parity-green: they are the A/B record of DESIGN.md §9."""
+    g = golden(name)
+    m = vocoder(cfg, g["seed"], g["weight_norm"], "bf16")
+    try:
+        m.set_option(option, 0)
+        err = rel_l2(m(g["mel"].cuda()), g["wav"])
+    finally:
+        m.set_option(option, 1)
+    print(f"{name} bf16 {option}=0: rel-L2 vs reference {err:.3e}")
+    assert err < TOL_BF16
+
+
 @pytest.mark.parametrize("T", [1, 2, 5, 33, 64, 65, 200])
 def test_activation_kernel_edges(T):
     """Activation1d alone (replicate edges on both FIRs) against the oracle, down to one-sample signals."""
