@@ -72,7 +72,8 @@ int tvb_get_precision(const tvb_handle* h);
 /* Ablation / cross-check switches of the bf16 path: "attn_tc" and "conv_tc" (1 = tcgen05 kernel, default;
  * 0 = the CUDA-core kernel of the same op; both are GPU kernels of this library, there is no CPU path),
  * "gemm_2cta" (1 = CTA-pair tcgen05 GEMM, default; 0 = single-CTA tcgen05 GEMM), "gemm_mc" (1 = two CTA pairs per cluster
- * sharing the W tile by TMA multicast; 0 = independent pairs, default), "attn_v" (8 = attn8_tc.cuh, 7 = attn7_tc.cuh, 6 = attn6_tc.cuh, 5 = attn5_tc.cuh, 4 = attn4_tc.cuh,
+ * sharing the W tile by TMA multicast; 0 = independent pairs, default), "gemm_bn" (1 = the CTA-pair GEMM switches to 128-column tiles when
+ * the 256-column tiling would leave CTA pairs idle -- small batches, default; 0 = always 256-column tiles), "attn_v" (8 = attn8_tc.cuh, 7 = attn7_tc.cuh, 6 = attn6_tc.cuh, 5 = attn5_tc.cuh, 4 = attn4_tc.cuh,
  * 3 = attn_tc.cuh), "attn_poly" (attention v4: 0 = every exp2 on MUFU; 2/3/4 = one element pair in n on the FMA-pipe
  * polynomial), "ln_fuse" (2 = LayerNorm computed inside the residual GEMM epilogue by 8-CTA clusters; 1 = LayerNorm
  * kernel emits bf16 + row statistics and the residual GEMM epilogue re-normalises the fp32 stream; 0 = separate fp32 LayerNorm output), "ln1_fold" (with ln_fuse = 1: 1 = the LayerNorm between attention and FFN is folded into the FFN-in GEMM, default;

@@ -32,6 +32,7 @@ ABLATIONS = [
     dict(attn_poly=2), dict(attn_poly=3), dict(attn_poly=4),  # exp2 partly on the FMA pipe
     dict(ln_fuse=2), dict(ln_fuse=2, attn_tc=0, conv_tc=0),    # LayerNorm inside the residual GEMM epilogue (8-CTA clusters, DSMEM)
     dict(ln_fuse=1), dict(ln_fuse=0), dict(ln1_fold=0), dict(ln1_fold=0, zigzag=0), dict(pdl=0),
+    dict(gemm_bn=0), dict(gemm_bn=0, ln1_fold=0), dict(gemm_bn=1, ln1_fold=0),   # 256-column GEMM tiles at small M (the default there is 128)
     dict(),                                                  # shipping defaults
 ]
 

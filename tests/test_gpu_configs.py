@@ -70,6 +70,26 @@ def test_config3_long_form_30s_batch8():
 
 
 @pytest.mark.timeout(900)
+@pytest.mark.parametrize("T", [702, 1133])
+def test_gemm_tile_width_does_not_change_results(T):
+    """Small batches run the CTA-pair GEMMs with 128-column tiles (`gemm_bn`, picked from the row count), large ones with 256:
+    both must give the SAME bits (the bf16 path turns any fp32-rounding difference into a 3e-3 change of the velocity, which would
+    make an utterance's result depend on its batch size).  Multi-wave 128-column launches: tests/test_gpu_gemm.py."""
+    m = model(0, False, "bf16")
+    x, cond, z, L = _batch(5, [T], 272)
+    t = torch.tensor(0.61)
+    out = []
+    for bn in (1, 0):
+        m.set_option("gemm_bn", bn)
+        v, _ = m.sample(x.cuda(), z.cuda(), cond.cuda(), L, t, 1.0, True)
+        torch.cuda.synchronize()
+        out.append(v.clone())
+    m.set_option("gemm_bn", 1)
+    assert torch.isfinite(out[0]).all()
+    assert torch.equal(out[0], out[1])
+
+
+@pytest.mark.timeout(900)
 def test_config4_ragged_64_dailytalk_like():
     """configs[3]: 64 utterances, durations ~ LogNormal(ln 4.5 s, 0.6) clipped to [2, 20] s, uniform prompt."""
     rng = np.random.default_rng(1234)

@@ -46,7 +46,17 @@ def test_gemm_f32_epilogue(M, N, K):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("pair", [0, 0x100])
+@pytest.mark.parametrize("M,N,K", [(256, 128, 64), (256, 384, 128), (512, 256, 512), (1536, 1024, 1024), (1536, 4096, 1024),
+                                   (256, 1024, 4096), (74 * 256 * 2 + 256, 128, 256)])
+def test_gemm_pair_bn128_f32_epilogue(M, N, K):
+    """CTA-pair kernel with 128-column tiles (the small-batch tiling: cta_group::2, M=256, N=128)."""
+    ref, _, of, _ = _run(M, N, K, 4 | 0x400)
+    err = (of - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("pair", [0, 0x100, 0x400])
 @pytest.mark.parametrize("epi", [0, 1, 2, 3])
 def test_gemm_epilogues(epi, pair):
     M, N, K = 512, 1024, 1024

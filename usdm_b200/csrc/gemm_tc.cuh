@@ -50,7 +50,9 @@ struct GemmParams {
     const float2* ln_stats;   // [M] (mean, rstd) of the resid rows            (EPI_RESID_LN)
     const float* ln_g;        // [N] LayerNorm weight / bias of the residual's norm
     const float* ln_b;
-    float2* part;             // [M, 8] per-row partial (sum, sum of squares) over columns [128 q, 128 q + 128)   (*_ST write, FOLD reads)
+    float2* part;             // [M, 16] per-row partial (sum, sum of squares) over columns [64 q, 64 q + 64), N == 1024   (*_ST write, FOLD reads).
+                              // The grouping (and so every rounding of the row statistics) is the same for both tile widths: an utterance's
+                              // result must not depend on which width its batch size selected (batch invariance, tests/test_gpu_configs.py)
     const float* fold_c;      // [N] column sums of the folded weight                                              (EPI_FOLD_GELU)
     float2* stats_out;        // [M] (mean, rstd), written once per row by the n == 0 tiles                        (EPI_FOLD_GELU)
     int reverse;              // CTA-pair kernels: walk the 256-row blocks from the last to the first.  Consumers traverse opposite to
@@ -258,6 +260,7 @@ constexpr int G2_SMEM_EPI2 = G2_SMEM_EPI + G2_EPI_WARPS * G2_EPI_BUFS * G2_EPI_T
 constexpr int G2_SMEM_BAR = G2_SMEM_EPI2 + G2_EPI_WARPS * G2_EPI_BUFS * G2_EPI_TILE2;
 constexpr int G2_SMEM_BYTES = G2_SMEM_BAR + 1024 + 512;
 constexpr int G2_THREADS = 320;
+constexpr int G2_PART_N = 16;                                // entries per row of GemmParams::part
 
 struct Gemm2Maps {
     CUtensorMap a, a2, b;     // operands
@@ -272,8 +275,15 @@ struct Gemm2Maps {
 // (measured: the NP == 1 kernel saturates the L2->SM fabric at ~10 TB/s, i.e. ~1.2-1.3 PFLOP/s at 128 FLOP/B, profiles/r01).
 // A stage may be overwritten once BOTH pairs have consumed it: each pair leader's commit arrives on the empty barrier of all
 // four CTAs (barrier count NP).
-template <int EPI, int NP>
+// BN = accumulator columns per pair tile.  256: each CTA stages 128 W rows per k-block.  128 (NP == 1 only; tm.b = the box-64
+// weight map): half-width tiles for launches whose 256-wide tiling leaves most CTA pairs idle (M <= a few 256-row blocks, i.e. the
+// single-utterance requests of the reference app: N = 1024 gives 4 tiles per row block, 24 pairs of 74 busy at B = 1) -- the
+// host picks the width that needs fewer (waves x tile time), see linear().
+template <int EPI, int NP, int BN = 256>
 __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmParams& p) {
+    static_assert(BN == 256 || (BN == 128 && NP == 1), "tile width");
+    constexpr int kHalf = BN / 2;                     // accumulator columns (= W rows) owned by one CTA / one epilogue column half
+    constexpr uint32_t kStageTx = G2_A_BYTES + kHalf * GEMM_BK * 2;   // bytes one CTA receives per k-block
     extern __shared__ uint8_t smem_raw[];
     // identical carve-up in both CTAs (the dynamic smem base offset is the same for every CTA of a kernel)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -295,8 +305,8 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
     const uint32_t crank = cluster_ctarank();
     const uint32_t cta = crank & 1;                  // position inside the pair, 0 = leader
     const int pair_id = static_cast<int>(crank >> 1);
-    const int tiles_n = p.N / 256;
-    const int num_tiles = (p.M / (256 * NP)) * tiles_n;      // cluster tiles: NP vertically adjacent 256 x 256 tiles
+    const int tiles_n = p.N / BN;
+    const int num_tiles = (p.M / (256 * NP)) * tiles_n;      // cluster tiles: NP vertically adjacent 256 x BN tiles
     const int num_kb = p.K / GEMM_BK;
     const int cluster_id = blockIdx.x / (2 * NP), num_clusters = gridDim.x / (2 * NP);
     const int m_blocks = p.M / (256 * NP);
@@ -329,11 +339,11 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
             int stage = 0; uint32_t phase = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 const int m0 = tile_m0(tile) + static_cast<int>(cta) * 128;
-                const int n0 = (tile % tiles_n) * 256 + static_cast<int>(cta) * 128;
+                const int n0 = (tile % tiles_n) * BN + static_cast<int>(cta) * kHalf;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * G2_STAGE_BYTES;
-                    if (cta == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);   // bytes of BOTH CTAs
+                    if (cta == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageTx);   // bytes of BOTH CTAs
                     const int k0 = kb * GEMM_BK;
                     if (k0 < p.K1) tma_load_2d_2cta(sa, &tm.a, &full_bar[stage], k0, m0);
                     else           tma_load_2d_2cta(sa, &tm.a2, &full_bar[stage], k0 - p.K1, m0);
@@ -349,7 +359,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
         }
     } else if (warp_idx == 1) {
         if (cta == 0 && elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(256, 256);
+            constexpr uint32_t idesc = make_idesc_bf16(256, BN);
             int stage = 0; uint32_t phase = 0; int it = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
                 const int as = it & 1;
@@ -378,10 +388,11 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
         constexpr bool kResidLn = (EPI == EPI_RESID_LN || EPI == EPI_RESID_LN_ST);
         constexpr bool kResid = kResidPlain || kResidLn;
         constexpr int kChunkCols = kBf16Out ? 64 : 32;            // one staging tile row = 128 B
-        constexpr int kChunks = 128 / kChunkCols;                 // per warp per tile
+        constexpr int kChunks = kHalf / kChunkCols;               // per warp per tile
+        static_assert(!kStats || (kChunkCols == 32 && kChunks % 2 == 0), "row-statistics groups are pairs of 32-column chunks");
         const int ew = warp_idx - 2;
         const int quad = warp_idx & 3;
-        const int chalf = ew >> 2;                                // which 128 of the 256 accumulator columns
+        const int chalf = ew >> 2;                                // which half of the BN accumulator columns
         uint8_t* stg = smem + kSmemEpi + ew * G2_EPI_BUFS * G2_EPI_TILE;
         uint8_t* stg2 = smem + kSmemEpi2 + ew * G2_EPI_BUFS * G2_EPI_TILE2;   // only used (and only inside the budget) by the *_ST epilogues
         uint64_t* rb = rbar + ew * G2_EPI_BUFS;
@@ -391,7 +402,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
         uint32_t bpar = 0;                                        // (kc / G2_EPI_BUFS) & 1: parity of this buffer's residual barrier
         auto chunk_coords = [&](int tile, int c, int& col, int& row) {
             row = tile_m0(tile) + static_cast<int>(cta) * 128 + quad * 32;
-            col = (tile % tiles_n) * 256 + chalf * 128 + c * kChunkCols;
+            col = (tile % tiles_n) * BN + chalf * kHalf + c * kChunkCols;
         };
         if constexpr (kResid) {
             if (lane == 0 && cluster_id < num_tiles) {
@@ -406,15 +417,15 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
             const int as = it & 1;
             mbar_wait(&tfull_bar[as], (it >> 1) & 1);
             tc_fence_after();
-            const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256 + chalf * 128;
-            float ps1 = 0.f, ps2 = 0.f;                               // *_ST: this thread's partial row statistics over its 128 columns
+            const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256 + chalf * kHalf;
+            float ps1 = 0.f, ps2 = 0.f;                               // *_ST: this thread's partial row statistics over the current 64-column group
             float fa = 1.f, fb = 0.f;                                 // FOLD: rstd and -rstd * mean of this thread's row
             if constexpr (EPI == EPI_FOLD_GELU) {
                 const int frow = tile_m0(tile) + static_cast<int>(cta) * 128 + quad * 32 + lane;
-                const float4* pp = reinterpret_cast<const float4*>(p.part + static_cast<size_t>(frow) * 8);
+                const float4* pp = reinterpret_cast<const float4*>(p.part + static_cast<size_t>(frow) * G2_PART_N);
                 float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < G2_PART_N / 2; ++q) {
                     const float4 a = pp[q];
                     t1 += a.x + a.z; t2 += a.y + a.w;
                 }
@@ -500,6 +511,10 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                     if constexpr (kStats) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) { ps1 += v[j]; ps2 = fmaf(v[j], v[j], ps2); }
+                        if (c & 1) {                               // a 64-column group is complete (two 32-column chunks, summed in column order)
+                            p.part[static_cast<size_t>(row + lane) * G2_PART_N + (col >> 6)] = make_float2(ps1, ps2);
+                            ps1 = 0.f; ps2 = 0.f;
+                        }
                         // bf16 copy through its own staging tile (64-B rows, 16-B chunk j of row r at chunk j ^ ((r >> 1) & 3)) + TMA store:
                         // per-row direct stores cost +30 % on this GEMM (profiles/r01)
                         uint8_t* row2 = stg2 + buf * G2_EPI_TILE2 + lane * 64;
@@ -538,9 +553,6 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                 }
                 if (++buf == G2_EPI_BUFS) { buf = 0; bpar ^= 1; }
             }
-            if constexpr (kStats)
-                p.part[static_cast<size_t>(tile_m0(tile) + static_cast<int>(cta) * 128 + quad * 32 + lane) * 8 + (tile % tiles_n) * 2 + chalf] =
-                    make_float2(ps1, ps2);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], static_cast<uint32_t>(2 * pair_id));   // the pair leader's MMA thread owns accumulator reuse
@@ -556,10 +568,10 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
     }
 }
 
-template <int EPI>
+template <int EPI, int BN = 256>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_tc_kernel(const __grid_constant__ Gemm2Maps tm, const GemmParams p) {
-    gemm_pair_body<EPI, 1>(tm, p);
+    gemm_pair_body<EPI, 1, BN>(tm, p);
 }
 // Cluster of 4 = two CTA pairs sharing the W tile by TMA multicast; tm.b must be the box-64 weight map; M % 512 == 0.
 template <int EPI>

@@ -148,6 +148,7 @@ struct tvb_handle {
     int opt_graph = 1;          // 1 = small batches (<= 16384 packed rows) replay one estimator pass as a CUDA graph inside tvb_solve
                                 // (the pass is ~230 launches; at B = 1 the host cannot feed them fast enough), 0 = always launch directly
     int opt_zigzag = 1;         // bf16 path: row-block traversal alternates between producer and consumer kernels (L2 reuse)
+    int opt_gemm_bn = 1;        // CTA-pair GEMM: 1 = 128-column tiles when the 256-column tiling needs more (waves x tile width) -- small batches; 0 = always 256
     int opt_gemm_mc = 0;        // CTA-pair GEMM: 1 = clusters of two pairs sharing the W tile by TMA multicast, 0 = independent pairs (default:
                                 // measured 7 % slower with multicast, profiles/r01: the pair kernel is not L2->SM bound after all)
     int opt_attn_ptmem = 1;     // tcgen05 attention v3: 1 = P kept in tensor memory (TS MMA), 0 = P staged through shared memory
@@ -200,7 +201,7 @@ struct tvb_handle {
     Act hin, p1, slots[32], hbA, hbB, qkv, ctx, mid;
     float *xpre = nullptr, *xalt = nullptr, *hres = nullptr, *vbuf = nullptr;
     float2 *statsA = nullptr, *statsB = nullptr;       // per-row (mean, rstd) of the two LayerNorms in flight (ln_fuse)
-    float2* ln_part = nullptr;                         // [Mp, 8] partial row statistics (ln1_fold)
+    float2* ln_part = nullptr;                         // [Mp, 16] partial row statistics (ln1_fold), one entry per 64 columns
     float *z_work = nullptr, *z_hat = nullptr, *v_pred = nullptr;
     CUtensorMap tm_hin_halo, tm_p1_halo;         // positional-conv A operand maps with the halo (box 160 rows x 64 columns)
     CUtensorMap tm_base, tm_hin32;               // fp32 maps of `base` (residual of the frame-projection GEMM) and of hin.f32 (its output)
@@ -592,6 +593,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     else if (!strcmp(name, "conv_tc")) h->opt_conv_tc = value ? 1 : 0;
     else if (!strcmp(name, "gemm_2cta")) h->opt_gemm_2cta = value ? 1 : 0;
     else if (!strcmp(name, "gemm_mc")) h->opt_gemm_mc = value ? 1 : 0;
+    else if (!strcmp(name, "gemm_bn")) h->opt_gemm_bn = value ? 1 : 0;
     else if (!strcmp(name, "zigzag")) h->opt_zigzag = value ? 1 : 0;
     else if (!strcmp(name, "graph")) h->opt_graph = value ? 1 : 0;
     else if (!strcmp(name, "pdl")) h->opt_pdl = value ? 1 : 0;
@@ -710,7 +712,7 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
         TRY(alloc_f32(h, &h->xalt, static_cast<size_t>(rows) * H));
         TRY(alloc_f32(h, reinterpret_cast<float**>(&h->statsA), 2 * static_cast<size_t>(rows)));
         TRY(alloc_f32(h, reinterpret_cast<float**>(&h->statsB), 2 * static_cast<size_t>(rows)));
-        TRY(alloc_f32(h, reinterpret_cast<float**>(&h->ln_part), 16 * static_cast<size_t>(rows)));
+        TRY(alloc_f32(h, reinterpret_cast<float**>(&h->ln_part), 32 * static_cast<size_t>(rows)));
         TRY(alloc_f32(h, &h->hres, static_cast<size_t>(rows) * H));
         TRY(alloc_f32(h, &h->vbuf, static_cast<size_t>(rows) * std::max(nf, 256)));
         TRY(alloc_f32(h, &h->z_work, sn));
@@ -814,14 +816,14 @@ static int launch_gemm_tc(tvb_handle* h, int epi, const CUtensorMap& tmA, const 
     return fail(TVB_ERR_INVALID, "unknown epilogue %d", epi);
 }
 
-template <int EPI>
+template <int EPI, int BN = 256>
 static int launch_gemm2_tc_t(tvb_handle* h, const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st, int num_sms, int cat = PC_GEMM) {
     static bool attr = false;
     if (!attr) {
-        CK(cudaFuncSetAttribute(gemm2_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(gemm2_tc_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
         attr = true;
     }
-    const int tiles = (p.M / 256) * (p.N / 256);
+    const int tiles = (p.M / 256) * (p.N / BN);
     int grid = 2 * tiles < (num_sms & ~1) ? 2 * tiles : (num_sms & ~1);
     ProfScope ps(h, st, cat);
     cudaLaunchConfig_t cfg{};
@@ -830,7 +832,7 @@ static int launch_gemm2_tc_t(tvb_handle* h, const Gemm2Maps& maps, const GemmPar
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = (h && h->opt_pdl) ? 1 : 0;
-    CK(cudaLaunchKernelEx(&cfg, gemm2_tc_kernel<EPI>, maps, p));
+    CK(cudaLaunchKernelEx(&cfg, gemm2_tc_kernel<EPI, BN>, maps, p));
     if (h) h->launches++;
     return TVB_OK;
 }
@@ -874,21 +876,39 @@ static int launch_gemm4_tc(tvb_handle* h, int epi, const Gemm2Maps& maps, const 
     }
     return fail(TVB_ERR_INVALID, "unknown epilogue %d", epi);
 }
-// CTA-pair GEMM; maps.b must be the box-128 weight map, maps.out / maps.resid the epilogue maps of the destination.
-static int launch_gemm2_tc(tvb_handle* h, int epi, const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st, int num_sms, int cat = PC_GEMM) {
-    if (p.M % 256 || p.N % 256 || p.K % GEMM_BK || p.K1 % GEMM_BK) return fail(TVB_ERR_INVALID, "gemm shape %dx%dx%d not tileable by CTA pairs", p.M, p.N, p.K);
+// CTA-pair GEMM; maps.b must be the box-128 weight map (bn == 256) or the box-64 one (bn == 128), maps.out / maps.resid the epilogue
+// maps of the destination.
+static int launch_gemm2_tc(tvb_handle* h, int epi, const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st, int num_sms, int cat = PC_GEMM,
+                           int bn = 256) {
+    if (p.M % 256 || p.N % bn || p.K % GEMM_BK || p.K1 % GEMM_BK) return fail(TVB_ERR_INVALID, "gemm shape %dx%dx%d not tileable by CTA pairs", p.M, p.N, p.K);
+#define TVB_G2_CASE(E) case E: return bn == 128 ? launch_gemm2_tc_t<E, 128>(h, maps, p, st, num_sms, cat) : launch_gemm2_tc_t<E, 256>(h, maps, p, st, num_sms, cat);
     switch (epi) {
-        case EPI_BF16: return launch_gemm2_tc_t<EPI_BF16>(h, maps, p, st, num_sms, cat);
-        case EPI_GELU_BF16: return launch_gemm2_tc_t<EPI_GELU_BF16>(h, maps, p, st, num_sms, cat);
-        case EPI_RESID_F32: return launch_gemm2_tc_t<EPI_RESID_F32>(h, maps, p, st, num_sms, cat);
-        case EPI_DUAL: return launch_gemm2_tc_t<EPI_DUAL>(h, maps, p, st, num_sms, cat);
-        case EPI_F32: return launch_gemm2_tc_t<EPI_F32>(h, maps, p, st, num_sms, cat);
-        case EPI_RESID_LN: return launch_gemm2_tc_t<EPI_RESID_LN>(h, maps, p, st, num_sms, cat);
-        case EPI_RESID_F32_ST: return launch_gemm2_tc_t<EPI_RESID_F32_ST>(h, maps, p, st, num_sms, cat);
-        case EPI_RESID_LN_ST: return launch_gemm2_tc_t<EPI_RESID_LN_ST>(h, maps, p, st, num_sms, cat);
-        case EPI_FOLD_GELU: return launch_gemm2_tc_t<EPI_FOLD_GELU>(h, maps, p, st, num_sms, cat);
+        TVB_G2_CASE(EPI_BF16)
+        TVB_G2_CASE(EPI_GELU_BF16)
+        TVB_G2_CASE(EPI_RESID_F32)
+        TVB_G2_CASE(EPI_DUAL)
+        TVB_G2_CASE(EPI_F32)
+        TVB_G2_CASE(EPI_RESID_LN)
+        TVB_G2_CASE(EPI_RESID_F32_ST)
+        TVB_G2_CASE(EPI_RESID_LN_ST)
+        TVB_G2_CASE(EPI_FOLD_GELU)
     }
+#undef TVB_G2_CASE
     return fail(TVB_ERR_INVALID, "unknown epilogue %d", epi);
+}
+
+// Tile width of the CTA-pair GEMM for an [Mp, N] output: 256 columns, except when that tiling does not even fill one wave of
+// CTA pairs and 128-column tiles finish in fewer (waves x tile width) -- the single-utterance launches (B = 1, 5 s: 24 tiles
+// for N = 1024 on 74 pairs; attention-out 21.9 -> 17.8 us, FFN-out 36.0 -> 29.1 us, 84.6 -> 71.5 ms per 32-NFE solve).
+// Once every pair is busy the 128-column tile is the slower one (half the MMA work per A-tile fetch: FFN-in at B = 16 ran
+// 1.5 x longer with it, profiles/r01), so full waves always use 256.
+static int pair_gemm_bn(const tvb_handle* h, int Mp, int N) {
+    if (N % 256) return 128;
+    if (!h->opt_gemm_bn) return 256;
+    const int pairs = h->num_sms / 2;
+    const int tiles256 = (Mp / 256) * (N / 256);
+    auto cost = [&](int bn) { return (((Mp / 256) * (N / bn) + pairs - 1) / pairs) * bn; };
+    return (tiles256 <= pairs && cost(128) < cost(256)) ? 128 : 256;
 }
 
 // out_f32 / out (bf16) = LayerNorm(a W^T + b + resid; g, beta): residual GEMM with the norm in its epilogue (bf16 path, N == 1024).
@@ -953,10 +973,12 @@ static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, Li
         p.reverse = (rev && h->opt_zigzag) ? 1 : 0;
         const int e = epi == LE_PLAIN ? EPI_BF16 : epi == LE_GELU ? EPI_GELU_BF16 : epi == LE_RESID ? (ln ? EPI_RESID_LN : EPI_RESID_F32)
                     : epi == LE_RESID_ST ? (ln ? EPI_RESID_LN_ST : EPI_RESID_F32_ST) : epi == LE_FOLD_GELU ? EPI_FOLD_GELU : epi == LE_F32 ? EPI_F32 : EPI_DUAL;
+        const int bn = (h->opt_gemm_2cta && !h->opt_gemm_mc) ? pair_gemm_bn(h, Mp, lin.N) : 256;
         if (epi == LE_RESID_ST) p.part = h->ln_part;
         if (epi == LE_FOLD_GELU) { p.part = h->ln_part; p.stats_out = h->statsB; p.fold_c = lin.fold_c; }
         if ((epi == LE_RESID_ST || epi == LE_FOLD_GELU) && !(h->opt_gemm_2cta && !h->opt_gemm_mc && lin.N % 256 == 0))
             return fail(TVB_ERR_STATE, "internal: folded LayerNorm needs the CTA-pair GEMM");
+        if (epi == LE_RESID_ST && lin.N != 64 * G2_PART_N) return fail(TVB_ERR_STATE, "internal: partial row statistics are laid out for N == 1024");
         if (h->opt_gemm_2cta) {
             Gemm2Maps maps;
             maps.a = a.tm; maps.a2 = a2 ? a2->tm : a.tm; maps.b = lin.tm2;
@@ -968,7 +990,8 @@ static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, Li
                 maps.b = lin.tm3;
                 return launch_gemm4_tc(h, e, maps, p, st, cat);
             }
-            return launch_gemm2_tc(h, e, maps, p, st, h->num_sms, cat);
+            if (bn == 128) maps.b = lin.tm3;
+            return launch_gemm2_tc(h, e, maps, p, st, h->num_sms, cat, bn);
         }
         return launch_gemm_tc(h, e, a.tm, a2 ? a2->tm : a.tm, lin.tm, p, st, h->num_sms, cat);
     }
@@ -1358,10 +1381,11 @@ extern "C" int tvb_debug_gemm_bf16(int device, const void* a_dev, const void* w_
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(TVB_ERR_INVALID, "sm_100a device required");
     const bool mc = (epilogue & 0x200) != 0;
-    const bool pair = (epilogue & 0x100) != 0 || mc;
+    const bool bn128 = (epilogue & 0x400) != 0 && !mc;          // CTA-pair kernel with 128-column tiles
+    const bool pair = (epilogue & 0x100) != 0 || mc || bn128;
     CUtensorMap tmA, tmB;
     TRY(make_tmap(&tmA, a_dev, M, K, K, 128));
-    TRY(make_tmap(&tmB, w_dev, N, K, K, mc ? 64 : pair ? 128 : GEMM_BN));
+    TRY(make_tmap(&tmB, w_dev, N, K, K, (mc || bn128) ? 64 : pair ? 128 : GEMM_BN));
     GemmParams p{};
     p.M = M; p.N = N; p.K = K; p.K1 = K; p.bias = bias_dev; p.resid = resid_dev; p.out_f32 = out_f32_dev;
     p.out_bf16 = static_cast<bf16*>(out_bf16_dev); p.ld_out = N;
@@ -1375,7 +1399,7 @@ extern "C" int tvb_debug_gemm_bf16(int device, const void* a_dev, const void* w_
         else maps.resid = maps.out;
         if (e == EPI_DUAL) TRY(make_tmap(&maps.out2, out_bf16_dev, M, N, N, 32, 32, false, true));
         if (mc) return launch_gemm4_tc(nullptr, e, maps, p, static_cast<cudaStream_t>(stream));
-        return launch_gemm2_tc(nullptr, e, maps, p, static_cast<cudaStream_t>(stream), prop.multiProcessorCount);
+        return launch_gemm2_tc(nullptr, e, maps, p, static_cast<cudaStream_t>(stream), prop.multiProcessorCount, PC_GEMM, bn128 ? 128 : 256);
     }
     return launch_gemm_tc(nullptr, epilogue, tmA, tmA, tmB, p, static_cast<cudaStream_t>(stream), prop.multiProcessorCount);
 }
