@@ -415,12 +415,10 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
         int it = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
             const int as = it & 1;
-            mbar_wait(&tfull_bar[as], (it >> 1) & 1);
-            tc_fence_after();
-            const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256 + chalf * kHalf;
-            float ps1 = 0.f, ps2 = 0.f;                               // *_ST: this thread's partial row statistics over the current 64-column group
             float fa = 1.f, fb = 0.f;                                 // FOLD: rstd and -rstd * mean of this thread's row
             if constexpr (EPI == EPI_FOLD_GELU) {
+                // before the accumulator wait: the 16 partials of the row come through an L2 that the operand ring keeps saturated,
+                // and every N tile of the row block re-reads them -- behind the wait they cost FFN-in 16 % (profiles/r01)
                 const int frow = tile_m0(tile) + static_cast<int>(cta) * 128 + quad * 32 + lane;
                 const float4* pp = reinterpret_cast<const float4*>(p.part + static_cast<size_t>(frow) * G2_PART_N);
                 float t1 = 0.f, t2 = 0.f;
@@ -434,6 +432,10 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                 fa = rstd; fb = -rstd * mean;
                 if ((tile % tiles_n) == 0 && chalf == 0) p.stats_out[frow] = make_float2(mean, rstd);
             }
+            mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256 + chalf * kHalf;
+            float ps1 = 0.f, ps2 = 0.f;                               // *_ST: this thread's partial row statistics over the current 64-column group
 #pragma unroll 1
             for (int c = 0; c < kChunks; ++c, ++kc) {
                 uint8_t* tile_s = stg + buf * G2_EPI_TILE;
