@@ -50,9 +50,12 @@ struct GemmParams {
     const float2* ln_stats;   // [M] (mean, rstd) of the resid rows            (EPI_RESID_LN)
     const float* ln_g;        // [N] LayerNorm weight / bias of the residual's norm
     const float* ln_b;
-    float2* part;             // [M, 16] per-row partial (sum, sum of squares) over columns [64 q, 64 q + 64), N == 1024   (*_ST write, FOLD reads).
-                              // The grouping (and so every rounding of the row statistics) is the same for both tile widths: an utterance's
+    float2* part;             // [M, part_n] per-row partial (sum, sum of squares), N == 1024   (*_ST write, FOLD reads).  The unit is a 64-column
+                              // group g_q summed in column order.  A 256-column writer stores e_k = g_2k + g_2k+1 (part_n == 8, one entry per
+                              // 128 columns: 4 float4 per row for the reader); a 128-column writer owns only one group per warp and stores the
+                              // g_q themselves (part_n == 16), the reader then forms e_k.  Every rounding is the same either way: an utterance's
                               // result must not depend on which width its batch size selected (batch invariance, tests/test_gpu_configs.py)
+    int part_n;               // 8 or 16, see `part`
     const float* fold_c;      // [N] column sums of the folded weight                                              (EPI_FOLD_GELU)
     float2* stats_out;        // [M] (mean, rstd), written once per row by the n == 0 tiles                        (EPI_FOLD_GELU)
     int reverse;              // CTA-pair kernels: walk the 256-row blocks from the last to the first.  Consumers traverse opposite to
@@ -260,7 +263,6 @@ constexpr int G2_SMEM_EPI2 = G2_SMEM_EPI + G2_EPI_WARPS * G2_EPI_BUFS * G2_EPI_T
 constexpr int G2_SMEM_BAR = G2_SMEM_EPI2 + G2_EPI_WARPS * G2_EPI_BUFS * G2_EPI_TILE2;
 constexpr int G2_SMEM_BYTES = G2_SMEM_BAR + 1024 + 512;
 constexpr int G2_THREADS = 320;
-constexpr int G2_PART_N = 16;                                // entries per row of GemmParams::part
 
 struct Gemm2Maps {
     CUtensorMap a, a2, b;     // operands
@@ -417,15 +419,23 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
             const int as = it & 1;
             float fa = 1.f, fb = 0.f;                                 // FOLD: rstd and -rstd * mean of this thread's row
             if constexpr (EPI == EPI_FOLD_GELU) {
-                // before the accumulator wait: the 16 partials of the row come through an L2 that the operand ring keeps saturated,
-                // and every N tile of the row block re-reads them -- behind the wait they cost FFN-in 16 % (profiles/r01)
+                // before the accumulator wait: the partials of the row come through an L2 that the operand ring keeps saturated,
+                // and every N tile of the row block re-reads them (16 entries read behind the wait cost FFN-in 16 %, profiles/r01)
                 const int frow = tile_m0(tile) + static_cast<int>(cta) * 128 + quad * 32 + lane;
-                const float4* pp = reinterpret_cast<const float4*>(p.part + static_cast<size_t>(frow) * G2_PART_N);
+                const float4* pp = reinterpret_cast<const float4*>(p.part + static_cast<size_t>(frow) * p.part_n);
                 float t1 = 0.f, t2 = 0.f;
+                if (p.part_n == 8) {
 #pragma unroll
-                for (int q = 0; q < G2_PART_N / 2; ++q) {
-                    const float4 a = pp[q];
-                    t1 += a.x + a.z; t2 += a.y + a.w;
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 a = pp[q];                    // (e_2q, e_2q+1)
+                        t1 += a.x + a.z; t2 += a.y + a.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 a = pp[2 * q], b = pp[2 * q + 1];   // (g_4q, g_4q+1), (g_4q+2, g_4q+3)
+                        t1 += (a.x + a.z) + (b.x + b.z); t2 += (a.y + a.w) + (b.y + b.w);
+                    }
                 }
                 const float mean = t1 * (1.0f / 1024.0f);
                 const float rstd = rsqrtf(fmaxf(t2 * (1.0f / 1024.0f) - mean * mean, 0.f) + 1e-5f);
@@ -436,6 +446,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
             tc_fence_after();
             const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256 + chalf * kHalf;
             float ps1 = 0.f, ps2 = 0.f;                               // *_ST: this thread's partial row statistics over the current 64-column group
+            [[maybe_unused]] float pg1 = 0.f, pg2 = 0.f;              // ... and the finished first group (256-column tiles)
 #pragma unroll 1
             for (int c = 0; c < kChunks; ++c, ++kc) {
                 uint8_t* tile_s = stg + buf * G2_EPI_TILE;
@@ -514,7 +525,12 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
 #pragma unroll
                         for (int j = 0; j < 32; ++j) { ps1 += v[j]; ps2 = fmaf(v[j], v[j], ps2); }
                         if (c & 1) {                               // a 64-column group is complete (two 32-column chunks, summed in column order)
-                            p.part[static_cast<size_t>(row + lane) * G2_PART_N + (col >> 6)] = make_float2(ps1, ps2);
+                            if constexpr (BN == 256) {
+                                if (c == 1) { pg1 = ps1; pg2 = ps2; }  // first group of this warp's 128 columns
+                                else p.part[static_cast<size_t>(row + lane) * 8 + (col >> 7)] = make_float2(pg1 + ps1, pg2 + ps2);
+                            } else {
+                                p.part[static_cast<size_t>(row + lane) * 16 + (col >> 6)] = make_float2(ps1, ps2);
+                            }
                             ps1 = 0.f; ps2 = 0.f;
                         }
                         // bf16 copy through its own staging tile (64-B rows, 16-B chunk j of row r at chunk j ^ ((r >> 1) & 3)) + TMA store:

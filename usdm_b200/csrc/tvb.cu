@@ -149,6 +149,7 @@ struct tvb_handle {
                                 // (the pass is ~230 launches; at B = 1 the host cannot feed them fast enough), 0 = always launch directly
     int opt_zigzag = 1;         // bf16 path: row-block traversal alternates between producer and consumer kernels (L2 reuse)
     int opt_gemm_bn = 1;        // CTA-pair GEMM: 1 = 128-column tiles when the 256-column tiling needs more (waves x tile width) -- small batches; 0 = always 256
+    int ln_part_n = 8;          // entries per row the last *_ST GEMM wrote into ln_part (8: 256-column tiles, 16: 128-column tiles)
     int opt_gemm_mc = 0;        // CTA-pair GEMM: 1 = clusters of two pairs sharing the W tile by TMA multicast, 0 = independent pairs (default:
                                 // measured 7 % slower with multicast, profiles/r01: the pair kernel is not L2->SM bound after all)
     int opt_attn_ptmem = 1;     // tcgen05 attention v3: 1 = P kept in tensor memory (TS MMA), 0 = P staged through shared memory
@@ -201,7 +202,7 @@ struct tvb_handle {
     Act hin, p1, slots[32], hbA, hbB, qkv, ctx, mid;
     float *xpre = nullptr, *xalt = nullptr, *hres = nullptr, *vbuf = nullptr;
     float2 *statsA = nullptr, *statsB = nullptr;       // per-row (mean, rstd) of the two LayerNorms in flight (ln_fuse)
-    float2* ln_part = nullptr;                         // [Mp, 16] partial row statistics (ln1_fold), one entry per 64 columns
+    float2* ln_part = nullptr;                         // [Mp, <= 16] partial row statistics (ln1_fold), see GemmParams::part
     float *z_work = nullptr, *z_hat = nullptr, *v_pred = nullptr;
     CUtensorMap tm_hin_halo, tm_p1_halo;         // positional-conv A operand maps with the halo (box 160 rows x 64 columns)
     CUtensorMap tm_base, tm_hin32;               // fp32 maps of `base` (residual of the frame-projection GEMM) and of hin.f32 (its output)
@@ -974,11 +975,11 @@ static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, Li
         const int e = epi == LE_PLAIN ? EPI_BF16 : epi == LE_GELU ? EPI_GELU_BF16 : epi == LE_RESID ? (ln ? EPI_RESID_LN : EPI_RESID_F32)
                     : epi == LE_RESID_ST ? (ln ? EPI_RESID_LN_ST : EPI_RESID_F32_ST) : epi == LE_FOLD_GELU ? EPI_FOLD_GELU : epi == LE_F32 ? EPI_F32 : EPI_DUAL;
         const int bn = (h->opt_gemm_2cta && !h->opt_gemm_mc) ? pair_gemm_bn(h, Mp, lin.N) : 256;
-        if (epi == LE_RESID_ST) p.part = h->ln_part;
-        if (epi == LE_FOLD_GELU) { p.part = h->ln_part; p.stats_out = h->statsB; p.fold_c = lin.fold_c; }
+        if (epi == LE_RESID_ST) { p.part = h->ln_part; p.part_n = h->ln_part_n = (bn == 128) ? 16 : 8; }
+        if (epi == LE_FOLD_GELU) { p.part = h->ln_part; p.part_n = h->ln_part_n; p.stats_out = h->statsB; p.fold_c = lin.fold_c; }
         if ((epi == LE_RESID_ST || epi == LE_FOLD_GELU) && !(h->opt_gemm_2cta && !h->opt_gemm_mc && lin.N % 256 == 0))
             return fail(TVB_ERR_STATE, "internal: folded LayerNorm needs the CTA-pair GEMM");
-        if (epi == LE_RESID_ST && lin.N != 64 * G2_PART_N) return fail(TVB_ERR_STATE, "internal: partial row statistics are laid out for N == 1024");
+        if (epi == LE_RESID_ST && lin.N != 1024) return fail(TVB_ERR_STATE, "internal: partial row statistics are laid out for N == 1024");
         if (h->opt_gemm_2cta) {
             Gemm2Maps maps;
             maps.a = a.tm; maps.a2 = a2 ? a2->tm : a.tm; maps.b = lin.tm2;
