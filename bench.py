@@ -278,6 +278,7 @@ def main():
     fl = F.estimator_flops([w["T"] + 1] * (2 * w["B"]), MODEL_CFG)
     passes = w["nfe"]
     roof = None
+    roof_hbm = None
     kernels = None
     if not args.no_profile:
         model.set_option("profile", 1)
@@ -299,6 +300,15 @@ def main():
             ms = prof[k][0]
             if ms > 0:
                 kernels[k]["tflops"] = fl[k] * passes / (ms / 1e3) / 1e12
+        # the row kernel of the path against the HBM roofline: LayerNorm reads the fp32 rows and writes the bf16
+        # operand copy (6 B per element of the VALID tokens; per-row statistics and the dirty lines of the producer not counted)
+        ln_ms, ln_n = prof.get("layernorm", (0.0, 0))
+        if ln_ms > 0 and ln_n > 0:
+            ln_bytes = 2 * w["B"] * (w["T"] + 1) * MODEL_CFG["hidden_size"] * 6
+            gbs = ln_bytes / (ln_ms / ln_n / 1e3) / 1e9
+            roof_hbm = dict(bound="hbm", kernel="k_layernorm (fp32 rows -> bf16 + row statistics, 25 launches per pass)", achieved=gbs, peak=peaks["hbm"],
+                            unit="GB/s", frac=gbs / peaks["hbm"], bytes_per_launch=ln_bytes, avg_launch_ms=ln_ms / ln_n,
+                            peak_source=peaks["source"] + " hbm_gbs")
     step_tflops = fl["total"] * passes * args.steps / dev_s / 1e12      # per GPU: fl counts this rank's batch, dev_s is the max over ranks
 
     cpu = None
@@ -340,7 +350,7 @@ def main():
                     data="synthetic", config=bench_config(args, w), clocks=clocks,
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(x_host.numel() * 8 + cond_host.numel() * 4),
                              d2h_bytes_per_step=int(out_host.numel() * 4), timing="wall clock, max over ranks"),
-                    gpu_launches=int(launches), roofline=roof,
+                    gpu_launches=int(launches), roofline=roof, roofline_hbm=roof_hbm,
                     roofline_step=dict(bound="tensor", achieved=step_tflops, peak=peaks["sustained"], unit="TFLOP/s per GPU",
                                        frac=step_tflops / peaks["sustained"],
                                        note="algorithmic FLOPs of the whole solve (valid tokens) / device time"),
