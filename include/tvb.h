@@ -144,11 +144,17 @@ int64_t tvb_device_bytes(const tvb_handle* h);
  * a_dev bf16 [M,K], w_dev bf16 [N,K], bias_dev fp32 [N] or NULL, resid_dev fp32 [M,N] or NULL,
  * out_f32_dev fp32 [M,N] or NULL, out_bf16_dev bf16 [M,N] or NULL.  epilogue: 0 bf16, 1 gelu->bf16, 2 +resid->f32,
  * 3 f32+bf16, 4 f32; OR 0x100 to run the CTA-pair (cta_group::2) kernel (then M % 256 == 0), OR 0x200 for the
- * cluster-of-4 multicast kernel (then M % 512 == 0).
+ * cluster-of-4 multicast kernel (then M % 512 == 0), OR 0x400 for the CTA-pair kernel with 128-column tiles (M % 256 == 0,
+ * N % 128 == 0).
  * M % 128 == 0, N % 256 == 0, K % 64 == 0. */
 int tvb_debug_gemm_bf16(int device, const void* a_dev, const void* w_dev, const float* bias_dev, const float* resid_dev,
                         float* out_f32_dev, void* out_bf16_dev, int32_t M, int32_t N, int32_t K, int32_t epilogue,
                         void* stream);
+
+/* Host-logic test hook (no device needed): the tile width (256 or 128 columns) the CTA-pair GEMM uses for an output of
+ * `rows` x N on a device with `num_sms` SMs -- 128 only when the 256-column tiling does not fill one wave of CTA pairs and the
+ * narrow tiles need fewer (waves x width).  rows % 256 == 0, N % 128 == 0; negative = error. */
+int tvb_debug_pair_gemm_bn(int32_t num_sms, int32_t rows, int32_t N);
 
 /* Kernel-level test hook (tests/ only): the tcgen05 attention kernel alone on packed [rows, 3H] bf16 q|k|v rows (q pre-scaled
  * by head_dim^-0.5 * log2(e)); sequence s occupies rows [seq_start[s], seq_start[s] + seq_len[s]).  ctx_dev bf16 [rows, H].

@@ -86,3 +86,31 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f"{f} references the oracle"
                 assert "/root/reference" not in src
+
+
+def test_pair_gemm_tile_width_rule():
+    """Host logic of the CTA-pair GEMM's tile width (tvb.cu: pair_gemm_bn_rule) on a 148-SM device.  Full waves must stay on
+    256-column tiles (narrow tiles there cost configs[1] 11 %: QKV +29 %, FFN-in +53 %); launches below one wave
+    of the 74 CTA pairs take 128-column tiles when those need fewer (waves x width)."""
+    from usdm_b200 import engine
+    lib = engine.load_library()
+    bn = lambda rows, n: lib.tvb_debug_pair_gemm_bn(148, rows, n)
+    pad = lambda n_seq, tokens: n_seq * (-(-tokens // 256) * 256)        # every sequence is padded to whole 256-row blocks
+    # BASELINE configs[1] (2 x 16 sequences of 1134 tokens), configs[2] (2 x 8 x 2856), and a 64-utterance ragged batch: always 256
+    for rows in (pad(32, 1134), pad(16, 2856), pad(32, 862), pad(128, 700)):
+        for n in (256, 1024, 2048, 3072, 4096):
+            assert bn(rows, n) == 256, (rows, n)
+    # one 5 s utterance + 272-frame prompt under CFG (2 x 703 tokens -> 1536 rows): N = 1024 is 24 tiles on 74 pairs -> narrow tiles;
+    # QKV (72 tiles, a tie) stays wide
+    rows = pad(2, 703)
+    assert rows == 1536
+    assert bn(rows, 1024) == 128 and bn(rows, 256) == 128
+    assert bn(rows, 3072) == 256
+    assert bn(rows, 4096) == 256                  # 96 tiles > 74 pairs: a full wave exists
+    # N that only 128-column tiles can cover
+    assert bn(rows, 384) == 128
+    # the choice only depends on (rows, N): monotone hand-over to wide tiles as the batch grows
+    widths = [bn(256 * k, 1024) for k in range(1, 40)]
+    first_wide = widths.index(256)
+    assert all(w == 128 for w in widths[:first_wide]) and all(w == 256 for w in widths[first_wide:])
+    assert lib.tvb_debug_pair_gemm_bn(148, 100, 1024) < 0 and lib.tvb_debug_pair_gemm_bn(148, 256, 100) < 0

@@ -903,13 +903,16 @@ static int launch_gemm2_tc(tvb_handle* h, int epi, const Gemm2Maps& maps, const 
 // for N = 1024 on 74 pairs; attention-out 21.9 -> 17.8 us, FFN-out 36.0 -> 29.1 us, 84.6 -> 71.5 ms per 32-NFE solve).
 // Once every pair is busy the 128-column tile is the slower one (half the MMA work per A-tile fetch: FFN-in at B = 16 ran
 // 1.5 x longer with it, profiles/r01), so full waves always use 256.
-static int pair_gemm_bn(const tvb_handle* h, int Mp, int N) {
+static int pair_gemm_bn_rule(int num_sms, int Mp, int N) {
     if (N % 256) return 128;
-    if (!h->opt_gemm_bn) return 256;
-    const int pairs = h->num_sms / 2;
+    const int pairs = num_sms / 2;
     const int tiles256 = (Mp / 256) * (N / 256);
     auto cost = [&](int bn) { return (((Mp / 256) * (N / bn) + pairs - 1) / pairs) * bn; };
     return (tiles256 <= pairs && cost(128) < cost(256)) ? 128 : 256;
+}
+static int pair_gemm_bn(const tvb_handle* h, int Mp, int N) {
+    if (N % 256 == 0 && !h->opt_gemm_bn) return 256;
+    return pair_gemm_bn_rule(h->num_sms, Mp, N);
 }
 
 // out_f32 / out (bf16) = LayerNorm(a W^T + b + resid; g, beta): residual GEMM with the norm in its epilogue (bf16 path, N == 1024).
@@ -1374,6 +1377,11 @@ extern "C" int tvb_solve(tvb_handle* h, int32_t solver, const int64_t* x_dev, co
 // ----------------------------------------------------------------------------------------------------------------
 // test hooks
 // ----------------------------------------------------------------------------------------------------------------
+extern "C" int tvb_debug_pair_gemm_bn(int32_t num_sms, int32_t rows, int32_t N) {
+    if (num_sms < 2 || rows <= 0 || rows % 256 || N <= 0 || N % 128) return fail(TVB_ERR_INVALID, "bad argument");
+    return pair_gemm_bn_rule(num_sms, rows, N);
+}
+
 extern "C" int tvb_debug_gemm_bf16(int device, const void* a_dev, const void* w_dev, const float* bias_dev, const float* resid_dev,
                                    float* out_f32_dev, void* out_bf16_dev, int32_t M, int32_t N, int32_t K, int32_t epilogue, void* stream) {
     if (!a_dev || !w_dev) return fail(TVB_ERR_INVALID, "null argument");

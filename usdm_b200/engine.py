@@ -55,6 +55,7 @@ _SIGNATURES = {
     "tvb_debug_attention": (C.c_int, [C.c_int, _P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, _P, C.c_int32, C.c_int32, _P]),
     "tvb_debug_set_trace": (C.c_int, [_P]),
+    "tvb_debug_pair_gemm_bn": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     # include/tvb_vocoder.h
     "tvb_voc_create": (C.c_int, [C.POINTER(TvbVocConfig), C.c_int, C.POINTER(_P)]),
     "tvb_voc_destroy": (None, [_P]),
