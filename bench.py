@@ -148,11 +148,14 @@ def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # One reference-arm "step" is the bounded sample itself: ONE CFG estimator evaluation of one utterance of the workload (1 / nfe of
+    # that utterance's solve).  ms_per_step is its measured time (so steps x ms_per_step is the real timed region); `value` scales
+    # it to the metric: target frames of the utterance / (nfe evaluations), which is batch-size independent on the CPU.
     steps = max(1, args.steps)
-    warmup = max(1, min(args.warmup, 2))
+    warmup = max(0, args.warmup)
     fps, per_eval, cores, sample = cpu_reference_sample(w, steps, warmup)
     line = dict(metric=METRIC, value=fps, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warmup,
-                ms_per_step=per_eval * w["nfe"] * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                ms_per_step=per_eval * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference", config=bench_config(args, w),
                 cpu_baseline=dict(value=fps, unit=UNIT, cores=cores, kind="port", sample=sample),
                 e2e=dict(value=fps, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))

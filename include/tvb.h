@@ -114,6 +114,13 @@ int tvb_solve(tvb_handle* h, int32_t solver, const int64_t* x_dev, const float* 
               const float* t_span_host, float gradient_scale, int32_t speech_prompt,
               const float* prompt_noise_dev, float* out_mel_dev, float* step_v_dev, void* stream);
 
+/* Data errors that only a kernel can see.  The reference's nn.Embedding asserts device-side when a unit id is outside its
+ * table (networks.py:305); here the lookup is kept in range and a sticky per-handle flag is raised instead.  Because no compute
+ * call synchronises the device, the flag is reported by the NEXT tvb_estimator_forward / tvb_sample_cfg / tvb_solve on the
+ * handle, or by this function (call it after synchronising the stream to learn about the call just made):
+ * TVB_ERR_INVALID once, then cleared; TVB_OK otherwise.  Never synchronises. */
+int tvb_async_status(tvb_handle* h);
+
 /* ---- decoder glue either side of the sampler; stateless, no handle ----
  * Replaces: process_unit (util/model_util.py:50-54): repeat every unit `rep` (= sampling_rate // 50 = 441) times, cut into
  * windows of `hop` (= 256) samples, majority vote per window (ties -> smallest value, as torch.mode).

@@ -29,6 +29,8 @@ BIGVGAN_22K_80 = dict(
     num_mels=80, upsample_rates=[4, 4, 2, 2, 2, 2], upsample_kernel_sizes=[8, 8, 4, 4, 4, 4], upsample_initial_channel=1536,
     resblock="1", resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]],
     activation="snakebeta", snake_logscale=True, sampling_rate=22050, hop_size=256,
+    # audio front-end entries of the same published config.json (read through `vocoder.h` by get_mel, model_util.py:35-36)
+    n_fft=1024, win_size=1024, fmin=0, fmax=8000,
 )
 SMALL_CFG = dict(BIGVGAN_22K_80, upsample_initial_channel=192)       # same topology, 96..3 channels: CPU-sized parity cases
 

@@ -172,3 +172,68 @@ def test_generate_sharded_single_rank_on_gpu_inputs():
     for b, l in enumerate(L.tolist()):
         alone = gen_fn(x[b:b + 1, :l].cuda(), cond[b:b + 1, :, :l].contiguous().cuda(), torch.tensor([l]))
         assert rel_l2(full[b:b + 1, :, :l], alone) < 1e-6
+
+
+@pytest.mark.timeout(900)
+def test_unit_ids_outside_the_table_are_reported_not_dereferenced():
+    """The reference's nn.Embedding asserts device-side on ids outside [0, n_tokens] (networks.py:305).  Here the lookup stays in
+    range (no illegal address), the call's output is flagged invalid, and the flag surfaces without any device synchronisation
+    inside the library: through check_async() once the stream has been synchronised, or at the next sampling call."""
+    x, cond, L = _inputs(12, 2, 48, [48, 30], 16)
+    m = model(0, True, "bf16")
+    y = torch.randn(2, 80, 48, generator=torch.Generator().manual_seed(1))
+    t = torch.tensor([0.3, 0.3])
+    good = m.estimator(x.cuda(), y.cuda(), cond.cuda(), t, L)
+    torch.cuda.synchronize()
+    m.check_async()                                            # nothing pending
+    for bad_id in (10001, -1, 2 ** 40):
+        xb = x.clone()
+        xb[1, 7] = bad_id
+        out = m.estimator(xb.cuda(), y.cuda(), cond.cuda(), t, L)
+        torch.cuda.synchronize()                               # would raise on an illegal address
+        assert torch.isfinite(out).all()
+        with pytest.raises(ValueError, match="unit ids outside"):
+            m.check_async()
+        m.check_async()                                        # reported once, then cleared
+        m.estimator(xb.cuda(), y.cuda(), cond.cuda(), t, L)
+        torch.cuda.synchronize()
+        with pytest.raises(ValueError, match="unit ids outside"):      # ... or by the next call on the handle
+            m.estimator(x.cuda(), y.cuda(), cond.cuda(), t, L)
+    xu = x.clone()
+    xu[0, :] = 10000                                           # the unconditional id itself is a valid table row
+    m.estimator(xu.cuda(), y.cuda(), cond.cuda(), t, L)
+    torch.cuda.synchronize()
+    m.check_async()
+    again = m.estimator(x.cuda(), y.cuda(), cond.cuda(), t, L)
+    assert torch.equal(good, again)
+
+
+@pytest.mark.timeout(900)
+def test_second_device_in_the_same_process():
+    """Kernel attributes (the > 48 KB dynamic shared-memory opt-in) are per device: a handle created on another GPU of the same
+    process must set them up again.  Needs two devices (gpurun --gpus 2); skipped otherwise."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    import usdm_b200
+    x, cond, L = _inputs(13, 2, 64, [64, 40], 16)
+    y = torch.randn(2, 80, 64, generator=torch.Generator().manual_seed(2))
+    t = torch.tensor([0.4, 0.4])
+    m0 = model(0, True, "bf16")
+    v0 = m0.estimator(x.cuda(0), y.cuda(0), cond.cuda(0), t, L)
+    m1 = usdm_b200.Voicebox(**CFG)
+    m1.load_state_dict(weights(0, True))
+    with torch.cuda.device(1):
+        v1 = m1.estimator(x.cuda(1), y.cuda(1), cond.cuda(1), t, L)
+        z = m1.generate(x.cuda(1), cond.cuda(1), L, 2, solver="heun", gradient_scale=1.0, speech_prompt=True, prompt_lengths=torch.tensor([16]))
+        torch.cuda.synchronize(1)
+    torch.cuda.synchronize(0)
+    assert torch.isfinite(z).all()
+    assert torch.equal(v0.cpu(), v1.cpu())                     # same bits on both devices
+    from oracle import vocoder_oracle as V
+    voc = usdm_b200.BigVGAN(V.SMALL_CFG)
+    voc.load_state_dict(V.init_vocoder_weights(11, V.SMALL_CFG))
+    mel = torch.randn(1, 80, 24, generator=torch.Generator().manual_seed(3))
+    w0 = voc.cuda(0)(mel.cuda(0)).cpu()
+    with torch.cuda.device(1):
+        w1 = voc.cuda(1)(mel.cuda(1)).cpu()
+    assert torch.equal(w0, w1)

@@ -22,6 +22,24 @@ __global__ void k(long long* out, float seed, int iters) {
             if (OP == 4) { uint32_t r; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a[i]), "f"(a[(i + 1) & 7])); a[i] = __uint_as_float(r); }
             if (OP == 5) asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(a[(i + 1) & 7]), "f"(seed));
             if (OP == 6) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(seed));
+            // packed half-precision exponentials: two results per lane and instruction
+            if (OP == 7) { uint32_t r = __float_as_uint(a[i]); asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(r)); a[i] = __uint_as_float(r); }
+            if (OP == 8) { uint32_t r = __float_as_uint(a[i]); asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(r)); a[i] = __uint_as_float(r); }
+            if (OP == 9) { uint32_t r; asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a[i]), "f"(a[(i + 1) & 7])); a[i] = __uint_as_float(r); }
+            if (OP == 10) { uint32_t r = __float_as_uint(a[i]); asm volatile("fma.rn.f16x2 %0, %0, %1, %1;" : "+r"(r) : "r"(__float_as_uint(seed))); a[i] = __uint_as_float(r); }
+            if (OP == 11) {      // MUFU + FFMA2 interleaved 1:1 (do the two pipes overlap?)
+                asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(p[i]) : "l"(c2));
+            }
+            if (OP == 12) {      // f16x2 MUFU + FFMA2 + pack, the mix of a packed-exponential softmax (per 2 elements)
+                uint32_t r;
+                asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(c2));
+                float lo, hi; asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p[i]));
+                asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+                asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(r));
+                a[i] = __uint_as_float(r);
+            }
+            if (OP == 13) { uint32_t r = __float_as_uint(a[i]); asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(r)); a[i] = __uint_as_float(r); }
         }
     }
     const long long t1 = clock64();
@@ -49,5 +67,12 @@ int main() {
     run<4>("F2FP.BF16 pack");
     run<5>("FMNMX3 (max.f32 3-input)");
     run<6>("FADD");
+    run<7>("MUFU.EX2 f16x2");
+    run<8>("MUFU.EX2 bf16x2");
+    run<9>("F2FP.F16 pack");
+    run<10>("HFMA2 (f16x2)");
+    run<11>("MUFU.EX2 f32 + FFMA2 pair");
+    run<12>("FADD2 + F2FP.F16 + EX2.f16x2");
+    run<13>("MUFU.TANH f16x2");
     return 0;
 }

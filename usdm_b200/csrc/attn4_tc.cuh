@@ -429,11 +429,11 @@ inline long long*& attn_trace_ptr() {      // test hook (tvb_debug_set_trace): d
 template <int POLY>
 inline cudaError_t launch_attn4_t(const CUtensorMap& tmQKV, __nv_bfloat16* ctx, int H, int nheads, const float* slopes, const int4* work,
                                   int nwork, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (!attr.done()) {
         cudaError_t e = cudaFuncSetAttribute(attn4_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr = true;
+        attr.mark();
     }
     attn4_kernel<POLY><<<nwork * nheads, ATT_THREADS, A4_SMEM_BYTES, st>>>(tmQKV, ctx, H, nheads, slopes, work, attn_trace_ptr());
     return cudaGetLastError();

@@ -317,11 +317,11 @@ attn5_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
 template <int POLY>
 inline cudaError_t launch_attn5_t(const CUtensorMap& tmQKV, __nv_bfloat16* ctx, int H, int nheads, const float* slopes, const int4* work,
                                   int nwork, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (!attr.done()) {
         cudaError_t e = cudaFuncSetAttribute(attn5_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, A5_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr = true;
+        attr.mark();
     }
     attn5_kernel<POLY><<<nwork * nheads, A5_THREADS, A5_SMEM_BYTES, st>>>(tmQKV, ctx, H, nheads, slopes, work);
     return cudaGetLastError();

@@ -449,11 +449,11 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
 template <int POLY>
 inline cudaError_t launch_attn6_t(const CUtensorMap& tmQKV, __nv_bfloat16* ctx, int H, int nheads, const float* slopes, const int4* work,
                                   int nwork, int num_sms, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (!attr.done()) {
         cudaError_t e = cudaFuncSetAttribute(attn6_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr = true;
+        attr.mark();
     }
     const int n_items = nwork * nheads;
     const int grid = n_items < num_sms ? n_items : num_sms;

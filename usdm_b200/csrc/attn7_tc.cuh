@@ -401,11 +401,11 @@ attn7_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
 template <int POLY>
 inline cudaError_t launch_attn7_t(const CUtensorMap& tmQKV, __nv_bfloat16* ctx, int H, int nheads, const float* slopes, const int4* work,
                                   int nwork, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (!attr.done()) {
         cudaError_t e = cudaFuncSetAttribute(attn7_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr = true;
+        attr.mark();
     }
     attn7_kernel<POLY><<<nwork * nheads, ATT_THREADS, A4_SMEM_BYTES, st>>>(tmQKV, ctx, H, nheads, slopes, work, attn_trace_ptr());
     return cudaGetLastError();

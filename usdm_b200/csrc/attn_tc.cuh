@@ -336,13 +336,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
 
 inline cudaError_t launch_attn_tc_raw(const CUtensorMap& tmQKV, __nv_bfloat16* ctx, int H, int nheads, const float* slopes,
                                       const int4* work, int nwork, bool p_in_tmem, float qk_scale, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (!attr.done()) {
         cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr = true;
+        attr.mark();
     }
     dim3 grid(nwork, nheads);
     if (p_in_tmem) attn_tc_kernel<true><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, ctx, H, slopes, work, qk_scale);

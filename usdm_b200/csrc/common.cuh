@@ -5,8 +5,33 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 
 namespace tvb {
+
+// ------------------------------------------------------------------------------------------
+// Host side: per-DEVICE one-time set-up.  cudaFuncSetAttribute (the > 48 KB dynamic shared-memory opt-in) and occupancy answers
+// belong to the device that was current when they were made; one process may hold handles on several GPUs (tvb_create takes a
+// device index), so the "already done" state is one bit / one value per device ordinal, updated atomically (the set-up itself is
+// idempotent, two threads racing on the same device only repeat it).
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & (kMaxDevices - 1);
+}
+struct PerDeviceOnce {
+    std::atomic<uint64_t> bits{0};
+    bool done() const { return (bits.load(std::memory_order_acquire) >> current_device_slot()) & 1ull; }
+    void mark() { bits.fetch_or(1ull << current_device_slot(), std::memory_order_release); }
+};
+struct PerDeviceInt {                                  // 0 = not computed yet on that device
+    std::atomic<int> v[kMaxDevices];
+    PerDeviceInt() { for (auto& x : v) x.store(0, std::memory_order_relaxed); }
+    int get() const { return v[current_device_slot()].load(std::memory_order_acquire); }
+    void set(int x) { v[current_device_slot()].store(x, std::memory_order_release); }
+};
 
 // ------------------------------------------------------------------------------------------
 // small utilities

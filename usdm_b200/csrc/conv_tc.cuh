@@ -298,13 +298,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX /* box 64 x 160 */, con
 inline cudaError_t launch_conv_halo_raw(const CUtensorMap& tmX160, const CUtensorMap& tmW, const float* bias, const int* row_seq, int Mp, int H,
                                         int taps, int groups, __nv_bfloat16* out_bf16, float* out_f32, const float* resid, int num_sms,
                                         cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (!attr.done()) {
         cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr = true;
+        attr.mark();
     }
     const int tiles = (Mp / 256) * groups;
     const int grid = tiles < num_sms ? tiles : num_sms;
@@ -318,13 +318,13 @@ inline cudaError_t launch_conv_halo_raw(const CUtensorMap& tmX160, const CUtenso
 inline cudaError_t launch_conv_tc_raw(const CUtensorMap& tmX, const CUtensorMap& tmW, const float* bias, const int* row_seq, int Mp, int H,
                                       int taps, int groups, __nv_bfloat16* out_bf16, float* out_f32, const float* resid, int num_sms,
                                       cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (!attr.done()) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr = true;
+        attr.mark();
     }
     const int tiles = (Mp / CV_BM) * groups;
     const int grid = tiles < num_sms ? tiles : num_sms;

@@ -58,6 +58,9 @@ struct GemmParams {
     int part_n;               // 8 or 16, see `part`
     const float* fold_c;      // [N] column sums of the folded weight                                              (EPI_FOLD_GELU)
     float2* stats_out;        // [M] (mean, rstd), written once per row by the n == 0 tiles                        (EPI_FOLD_GELU)
+    float* rownorm;           // EPI_BF16, CTA-pair kernels: when set, normtab[row / 32][col / 64] = max over the 32 rows of the squared norm of the 64
+    int rownorm_cols;         //   output columns (fp32 values before the bf16 rounding), for columns < rownorm_cols: the |q|, |k| row-block maxima
+    int rownorm_ld;           //   the attention kernel bounds its logits with (attn9_tc.cuh); row stride rownorm_ld
     int reverse;              // CTA-pair kernels: walk the 256-row blocks from the last to the first.  Consumers traverse opposite to
                               // the kernel that produced their input, so the rows they read first are the ones still in the 126 MB L2.
 };
@@ -391,6 +394,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
         constexpr bool kResid = kResidPlain || kResidLn;
         constexpr int kChunkCols = kBf16Out ? 64 : 32;            // one staging tile row = 128 B
         constexpr int kChunks = kHalf / kChunkCols;               // per warp per tile
+        static_assert(G2_EPI_BUFS == 2, "the residual prefetch below assumes two staging buffers per warp");
         static_assert(!kStats || (kChunkCols == 32 && kChunks % 2 == 0), "row-statistics groups are pairs of 32-column chunks");
         const int ew = warp_idx - 2;
         const int quad = warp_idx & 3;
@@ -453,11 +457,18 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                 const int nbuf = (buf + 1 == G2_EPI_BUFS) ? 0 : buf + 1;
                 int col, row;
                 chunk_coords(tile, c, col, row);
+                // The accumulator chunk is requested first: the staging-buffer bookkeeping below (one lane waiting for a TMA store to
+                // finish reading shared memory) then overlaps the TMEM load instead of preceding it.
+                uint32_t racc[kChunkCols / 32][32];
+#pragma unroll
+                for (int q = 0; q < kChunkCols / 32; ++q) tmem_ld_32x32(t_acc + c * kChunkCols + q * 32, racc[q]);
                 if (lane == 0) {
                     if constexpr (kResid) {
-                        // buffer nbuf was last used by the chunk two back: its store must have finished reading before the next
-                        // residual tile lands there (the store of the previous chunk may still be in flight)
-                        tma_store_wait_read<1>();
+                        // The next chunk's residual tile is prefetched into staging buffer nbuf, which (two buffers) was last read by the
+                        // TMA store of the PREVIOUS chunk - the most recent bulk group.  Every committed store must therefore have
+                        // finished reading its source before the load is issued: wait_group.read 0 (a store reads its 4 + 2 KB within a
+                        // few hundred cycles, behind the TMEM load issued above).  <1> here was a write-after-read on nbuf.
+                        tma_store_wait_read<G2_EPI_BUFS - 2>();
                         int nt = tile, nc = c + 1;
                         if (nc == kChunks) { nc = 0; nt = tile + num_clusters; }
                         if (nt < num_tiles) {
@@ -474,11 +485,9 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                 float v[kChunkCols];
 #pragma unroll
                 for (int q = 0; q < kChunkCols / 32; ++q) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(t_acc + c * kChunkCols + q * 32, r);
-                    tmem_ld_wait();
+                    tmem_ld_wait_dep(racc[q]);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[q * 32 + j] = __uint_as_float(r[j]);
+                    for (int j = 0; j < 32; ++j) v[q * 32 + j] = __uint_as_float(racc[q][j]);
                 }
                 if constexpr (EPI == EPI_FOLD_GELU) {
                     const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
@@ -544,6 +553,15 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                                            pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
                     }
                 } else if constexpr (kBf16Out) {
+                    if constexpr (EPI == EPI_BF16) {
+                        if (p.rownorm != nullptr && col < p.rownorm_cols) {      // one 64-column chunk = one head of q or k
+                            float ss = 0.f;
+#pragma unroll
+                            for (int j = 0; j < kChunkCols; ++j) ss = fmaf(v[j], v[j], ss);
+                            const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(ss));
+                            if (lane == 0) p.rownorm[static_cast<size_t>(row >> 5) * p.rownorm_ld + (col >> 6)] = __uint_as_float(mx);
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<uint4*>(rowp + ((j ^ r7) << 4)) =

@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(256)
 k_frame_proj(RowLayout L, int T, int nf, int H, const float* __restrict__ Wt, const float* __restrict__ src,
              const int64_t* __restrict__ x, const float* __restrict__ G, const float* __restrict__ b_in, int uncond_id,
              int src_is_zero, const float* __restrict__ base, const float* __restrict__ t_seq, float t_uniform,
-             const float* __restrict__ freqs, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+             const float* __restrict__ freqs, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
+             int* __restrict__ err_flag = nullptr) {
     extern __shared__ float s_src[];   // [nf][FP_ROWS]
     __shared__ int s_seq[FP_ROWS], s_pos[FP_ROWS];
     const int r0 = blockIdx.x * FP_ROWS;
@@ -65,7 +66,13 @@ k_frame_proj(RowLayout L, int T, int nf, int H, const float* __restrict__ Wt, co
             if (seq >= 0) {
                 if (PREP) {
                     if (pos >= 1) {
-                        const int64_t id = L.seq_uncond[seq] ? uncond_id : x[static_cast<size_t>(L.seq_utt[seq]) * T + (pos - 1)];
+                        int64_t id = L.seq_uncond[seq] ? uncond_id : x[static_cast<size_t>(L.seq_utt[seq]) * T + (pos - 1)];
+                        // nn.Embedding asserts device-side on an id outside its table (networks.py:305); here the lookup stays inside
+                        // G (the unconditional row stands in) and the handle's sticky flag reports the call as invalid
+                        if (id < 0 || id > uncond_id) {
+                            if (err_flag && n == 0) *err_flag = 1;
+                            id = uncond_id;
+                        }
                         const float4 g = *reinterpret_cast<const float4*>(G + static_cast<size_t>(id) * H + n);
                         const float4 b = *reinterpret_cast<const float4*>(b_in + n);
                         a = make_float4(g.x + b.x, g.y + b.y, g.z + b.z, g.w + b.w);

@@ -22,6 +22,7 @@
 #include "attn6_tc.cuh"
 #include "attn7_tc.cuh"
 #include "attn8_tc.cuh"
+#include "attn9_tc.cuh"
 #include <algorithm>
 #include "conv_tc.cuh"
 #include "gemm_tc.cuh"
@@ -133,6 +134,8 @@ struct tvb_handle {
     bool finalized = false;
     int num_sms = 148;
     int64_t launches = 0;
+    int* err_host = nullptr;    // mapped pinned word that kernels set when they meet invalid DATA (unit ids outside the table); host-visible
+    int* err_dev = nullptr;     //   without a device synchronisation, checked and cleared by tvb_async_status / the next compute call
     size_t dev_bytes = 0;       // weights
     size_t ws_bytes = 0;        // workspace
     int opt_attn_tc = 1;        // bf16 path: 1 = tcgen05 attention, 0 = CUDA-core attention (ablation / cross-check)
@@ -153,7 +156,12 @@ struct tvb_handle {
     int opt_gemm_mc = 0;        // CTA-pair GEMM: 1 = clusters of two pairs sharing the W tile by TMA multicast, 0 = independent pairs (default:
                                 // measured 7 % slower with multicast, profiles/r01: the pair kernel is not L2->SM bound after all)
     int opt_attn_ptmem = 1;     // tcgen05 attention v3: 1 = P kept in tensor memory (TS MMA), 0 = P staged through shared memory
-    int opt_attn_v = 8;         // tcgen05 attention kernel generation: 8 = attn8_tc.cuh (default), 7 .. 4 = attnN_tc.cuh, 3 = attn_tc.cuh
+    int opt_attn_v = 9;         // tcgen05 attention kernel generation: 9 = attn9_tc.cuh (default), 8 .. 4 = attnN_tc.cuh, 3 = attn_tc.cuh
+    int opt_attn_win = 1;       // attention v9: 1 = key blocks whose probabilities are provably below 2^-40 of the row sum are skipped (ALiBi
+                                // window, attn9_tc.cuh), 0 = every key block is processed (ablation / exactness check)
+    float* normtab = nullptr;   // attention v9: [rows / 32][2 heads] row-block maxima of |q|^2, |k|^2, written by the QKV GEMM epilogue
+    int4* d_win = nullptr;      //   and the per-item (tile, head) windows / reference shifts derived from them (k_attn9_plan)
+    bool norm_from_gemm = false;   // the last QKV GEMM filled normtab (otherwise attention() runs k_attn9_rownorm)
     int opt_attn_pace = 0;      // attention v8: 1 = MUFU pairs paced by an earlier pair's tail (forces ptxas to interleave the pipes in program
                                 // order; measured 2-15 % SLOWER: the added dependency latency outweighs it), 0 = free order (default)
     int opt_attn_poly = 3;      // attention v4+: 0 = every exp2 on MUFU, n = one element pair in n on the FMA-pipe polynomial (default 3)
@@ -301,8 +309,37 @@ extern "C" int tvb_create(const tvb_config* cfg, int device, tvb_handle** out) {
     h->cfg = c;
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h->err_host), 64, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->err_dev), h->err_host, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (h->err_host) cudaFreeHost(h->err_host);
+        delete h;
+        return fail(TVB_ERR_NOMEM, "cannot allocate the mapped status word");
+    }
+    for (int i = 0; i < 16; ++i) h->err_host[i] = 0;
     *out = h;
     return TVB_OK;
+}
+
+// Data errors found by kernels of EARLIER calls (no call synchronises the device to look for them): reported once, then cleared.
+static int take_async_error(tvb_handle* h) {
+    volatile int* f = h->err_host;
+    if (f && f[0]) {
+        f[0] = 0;
+        return fail(TVB_ERR_INVALID, "a previous call was given unit ids outside [0, n_tokens = %d]; its output is invalid "
+                                     "(the reference's nn.Embedding asserts on such ids, networks.py:305)", h->cfg.n_tokens);
+    }
+    if (f && f[1]) {
+        f[1] = 0;
+        return fail(TVB_ERR_INVALID, "a previous call produced attention logits beyond the range the tcgen05 attention kernel supports "
+                                     "(2 max|q| max|k| > %g in the log2 domain, or non-finite activations); its output is invalid -- "
+                                     "set option attn_v = 8 for such weights", static_cast<double>(A9_LOGIT_LIMIT));
+    }
+    return TVB_OK;
+}
+extern "C" int tvb_async_status(tvb_handle* h) {
+    if (!h) return fail(TVB_ERR_INVALID, "null handle");
+    return take_async_error(h);
 }
 
 extern "C" int tvb_destroy(tvb_handle* h) {
@@ -312,6 +349,7 @@ extern "C" int tvb_destroy(tvb_handle* h) {
     for (void* p : h->owned) cudaFree(p);
     for (void* p : h->ws_owned) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->err_host) cudaFreeHost(h->err_host);
     drop_graphs(h);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     delete h;
@@ -603,7 +641,8 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     else if (!strcmp(name, "conv_halo")) h->opt_conv_halo = value ? 1 : 0;
     else if (!strcmp(name, "ln1_fold")) h->opt_ln1_fold = value ? 1 : 0;
     else if (!strcmp(name, "attn_ptmem")) h->opt_attn_ptmem = value ? 1 : 0;
-    else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 8) return fail(TVB_ERR_INVALID, "attn_v must be 3 .. 8"); h->opt_attn_v = value; }
+    else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 9) return fail(TVB_ERR_INVALID, "attn_v must be 3 .. 9"); h->opt_attn_v = value; }
+    else if (!strcmp(name, "attn_win")) h->opt_attn_win = value ? 1 : 0;
     else if (!strcmp(name, "attn_poly")) { if (value != 0 && value != 2 && value != 3 && value != 4 && !(value >= 100 && value < 108)) return fail(TVB_ERR_INVALID, "attn_poly must be 0, 2, 3 or 4"); h->opt_attn_poly = value; }
     else if (!strcmp(name, "attn_pace")) h->opt_attn_pace = value ? 1 : 0;
     else if (!strcmp(name, "ln_fuse")) { if (value < 0 || value > 2) return fail(TVB_ERR_INVALID, "ln_fuse must be 0, 1 or 2"); h->opt_ln_fuse = value; }
@@ -708,6 +747,8 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
         TRY(dev_alloc_t(h, h->ws_owned, &h->d_work16, w16c));
         TRY(dev_alloc_t(h, h->ws_owned, &h->d_work128, w128c));
         TRY(dev_alloc_t(h, h->ws_owned, &h->d_tseq, sc));
+        TRY(alloc_f32(h, &h->normtab, static_cast<size_t>(rows / 32 + 1) * 2 * c.num_attention_heads));
+        TRY(dev_alloc_t(h, h->ws_owned, &h->d_win, static_cast<size_t>(w128c) * c.num_attention_heads));
         TRY(alloc_f32(h, &h->base, static_cast<size_t>(rows) * H));
         TRY(alloc_f32(h, &h->xpre, static_cast<size_t>(rows) * H));
         TRY(alloc_f32(h, &h->xalt, static_cast<size_t>(rows) * H));
@@ -790,10 +831,10 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
 template <int EPI>
 static int launch_gemm_tc_t(tvb_handle* h, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const GemmParams& p,
                             cudaStream_t st, int num_sms, int cat = PC_GEMM) {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (!attr.done()) {
         CK(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-        attr = true;
+        attr.mark();
     }
     const int tiles = (p.M / GEMM_BM) * (p.N / GEMM_BN);
     const int grid = tiles < num_sms ? tiles : num_sms;
@@ -819,10 +860,10 @@ static int launch_gemm_tc(tvb_handle* h, int epi, const CUtensorMap& tmA, const 
 
 template <int EPI, int BN = 256>
 static int launch_gemm2_tc_t(tvb_handle* h, const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st, int num_sms, int cat = PC_GEMM) {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (!attr.done()) {
         CK(cudaFuncSetAttribute(gemm2_tc_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
-        attr = true;
+        attr.mark();
     }
     const int tiles = (p.M / 256) * (p.N / BN);
     int grid = 2 * tiles < (num_sms & ~1) ? 2 * tiles : (num_sms & ~1);
@@ -839,7 +880,8 @@ static int launch_gemm2_tc_t(tvb_handle* h, const Gemm2Maps& maps, const GemmPar
 }
 template <int EPI>
 static int launch_gemm4_tc_t(tvb_handle* h, const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st, int cat) {
-    static int max_clusters = 0;
+    static PerDeviceInt max_clusters_dev;
+    int max_clusters = max_clusters_dev.get();
     if (max_clusters == 0) {
         CK(cudaFuncSetAttribute(gemm4_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
         cudaLaunchConfig_t cfg{};
@@ -854,6 +896,7 @@ static int launch_gemm4_tc_t(tvb_handle* h, const Gemm2Maps& maps, const GemmPar
         CK(cudaOccupancyMaxActiveClusters(&n, gemm4_tc_kernel<EPI>, &cfg));
         if (n < 1) return fail(TVB_ERR_CUDA, "no 4-CTA cluster fits on this device");
         max_clusters = n;
+        max_clusters_dev.set(n);
         if (getenv("TVB_DEBUG")) fprintf(stderr, "[tvb] gemm4_tc_kernel: %d resident 4-CTA clusters\n", n);
     }
     const int tiles = (p.M / 512) * (p.N / 256);
@@ -918,7 +961,8 @@ static int pair_gemm_bn(const tvb_handle* h, int Mp, int N) {
 // out_f32 / out (bf16) = LayerNorm(a W^T + b + resid; g, beta): residual GEMM with the norm in its epilogue (bf16 path, N == 1024).
 static int linear_ln(tvb_handle* h, const Lin& lin, const Act& a, const float* resid, float* out_f32, Act* out, const float* g,
                      const float* beta, cudaStream_t st, int cat) {
-    static int max_clusters = 0;
+    static PerDeviceInt max_clusters_dev;
+    int max_clusters = max_clusters_dev.get();
     if (max_clusters == 0) {
         CK(cudaFuncSetAttribute(gemmln_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM_BYTES));
         cudaLaunchConfig_t cfg{};
@@ -933,6 +977,7 @@ static int linear_ln(tvb_handle* h, const Lin& lin, const Act& a, const float* r
         CK(cudaOccupancyMaxActiveClusters(&n, gemmln_tc_kernel, &cfg));
         if (n < 1) return fail(TVB_ERR_CUDA, "no 8-CTA cluster of the fused GEMM+LayerNorm kernel fits on this device");
         max_clusters = n;
+        max_clusters_dev.set(n);
         if (getenv("TVB_DEBUG")) fprintf(stderr, "[tvb] gemmln_tc_kernel: %d resident 8-CTA clusters\n", n);
     }
     const int Mp = h->L.Mp;
@@ -975,6 +1020,10 @@ static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, Li
         p.bias = lin.bias_tc; p.resid = ln ? ln->x : resid; p.out_f32 = out_f32; p.out_bf16 = out ? out->b16 : nullptr; p.ld_out = lin.N;
         if (ln) { p.ln_stats = ln->stats; p.ln_g = ln->g; p.ln_b = ln->b; }
         p.reverse = (rev && h->opt_zigzag) ? 1 : 0;
+        if (cat == PC_GEMM_QKV) {         // attention v9 bounds its logits with row-block norms of q and k: the CTA-pair epilogue emits them
+            h->norm_from_gemm = h->opt_gemm_2cta && !h->opt_gemm_mc && epi == LE_PLAIN && lin.N == 3 * h->cfg.hidden_size;
+            if (h->norm_from_gemm) { p.rownorm = h->normtab; p.rownorm_cols = 2 * h->cfg.hidden_size; p.rownorm_ld = 2 * h->cfg.num_attention_heads; }
+        }
         const int e = epi == LE_PLAIN ? EPI_BF16 : epi == LE_GELU ? EPI_GELU_BF16 : epi == LE_RESID ? (ln ? EPI_RESID_LN : EPI_RESID_F32)
                     : epi == LE_RESID_ST ? (ln ? EPI_RESID_LN_ST : EPI_RESID_F32_ST) : epi == LE_FOLD_GELU ? EPI_FOLD_GELU : epi == LE_F32 ? EPI_F32 : EPI_DUAL;
         const int bn = (h->opt_gemm_2cta && !h->opt_gemm_mc) ? pair_gemm_bn(h, Mp, lin.N) : 256;
@@ -1041,7 +1090,16 @@ static int attention(tvb_handle* h, cudaStream_t st) {
     const int H = h->cfg.hidden_size, nh = h->cfg.num_attention_heads;
     ProfScope ps(h, st, PC_ATTN);
     // bf16 path: q carries head_dim^-0.5 * log2(e) (tvb_finalize_weights), so tensor-core scores are already in the log2 domain
-    if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 8) {
+    if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 9) {
+        if (!h->norm_from_gemm) {         // QKV GEMM variant without the row-norm epilogue: take the norms from its output
+            k_attn9_rownorm<<<(h->L.Mp + 31) / 32, 256, 0, st>>>(h->qkv.b16, h->L.Mp, H, nh, h->normtab);
+            h->launches++;
+            CKL();
+        }
+        CK(launch_attn9_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->normtab, h->d_win, h->opt_attn_win,
+                            h->err_dev + 1, h->opt_attn_poly, h->num_sms, st, h->opt_pdl != 0));
+        h->launches++;                    // k_attn9_plan
+    } else if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 8) {
         CK(launch_attn8_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_poly, h->num_sms, st, h->opt_attn_pace != 0, h->opt_pdl != 0));
     } else if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 7) {
         CK(launch_attn7_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_poly, st));
@@ -1115,7 +1173,7 @@ static int prep_base(tvb_handle* h, const int64_t* x, const float* cond, int con
     const size_t smem = static_cast<size_t>(c.n_feats) * FP_ROWS * sizeof(float);
     ProfScope ps(h, st, PC_FRAME);
     k_frame_proj<true><<<h->L.Mp / FP_ROWS, 256, smem, st>>>(h->L, h->plan_T, c.n_feats, c.hidden_size, h->Wc_t, cond, x, h->G, h->b_in,
-                                                             c.n_tokens, cond_is_zero, nullptr, nullptr, 0.f, nullptr, h->base, nullptr);
+                                                             c.n_tokens, cond_is_zero, nullptr, nullptr, 0.f, nullptr, h->base, nullptr, h->err_dev);
     h->launches++;
     CKL();
     return TVB_OK;
@@ -1280,6 +1338,7 @@ static int run_estimator_step(tvb_handle* h, const float* y, float t, cudaStream
 extern "C" int tvb_estimator_forward(tvb_handle* h, const int64_t* x_dev, const float* y_dev, const float* cond_dev, const float* t_host,
                                      const int64_t* lengths_host, int32_t B, int32_t T, float* out_v_dev, void* stream) {
     if (!h || !x_dev || !y_dev || !cond_dev || !t_host || !lengths_host || !out_v_dev) return fail(TVB_ERR_INVALID, "null argument");
+    TRY(take_async_error(h));
     CK(cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TRY(build_plan(h, B, T, lengths_host, 0, st));
@@ -1306,6 +1365,7 @@ static int ode_update(tvb_handle* h, const OdeParams& p, cudaStream_t st) {
 extern "C" int tvb_sample_cfg(tvb_handle* h, const int64_t* x_dev, const float* z_dev, const float* cond_dev, const int64_t* lengths_host,
                               int32_t B, int32_t T, float t, float gradient_scale, int32_t speech_prompt, float* out_v_dev, void* stream) {
     if (!h || !x_dev || !z_dev || !cond_dev || !lengths_host || !out_v_dev) return fail(TVB_ERR_INVALID, "null argument");
+    TRY(take_async_error(h));
     CK(cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int cfg = gradient_scale > 0.f ? 1 : 0;
@@ -1329,6 +1389,7 @@ extern "C" int tvb_solve(tvb_handle* h, int32_t solver, const int64_t* x_dev, co
     if (prompt_len < 0 || prompt_len > T) return fail(TVB_ERR_INVALID, "prompt_len %d outside [0, T]", prompt_len);
     const int P = speech_prompt ? prompt_len : 0;
     if (P > 0 && !prompt_noise_dev) return fail(TVB_ERR_INVALID, "prompt_noise_dev is required when speech_prompt and prompt_len > 0");
+    TRY(take_async_error(h));
     CK(cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int cfg = gradient_scale > 0.f ? 1 : 0;
@@ -1441,7 +1502,19 @@ extern "C" int tvb_debug_attention(int device, const void* qkv_dev, void* ctx_de
     int rc = make_tmap(&tm, qkv_dev, rows, 3 * H, 3 * H, 128);
     if (rc == TVB_OK) {
         cudaError_t e;
-        if (version == 8) e = launch_attn8_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, prop.multiProcessorCount, st);
+        if (version == 9 || version == 90) {     // 90: every key block (no ALiBi window)
+            float* normtab = nullptr; int4* win = nullptr;
+            e = cudaMalloc(&normtab, static_cast<size_t>(rows / 32 + 1) * 2 * nheads * sizeof(float));
+            if (e == cudaSuccess) e = cudaMalloc(&win, work.size() * nheads * sizeof(int4));
+            if (e == cudaSuccess) {
+                k_attn9_rownorm<<<(rows + 31) / 32, 256, 0, st>>>(static_cast<const bf16*>(qkv_dev), rows, H, nheads, normtab);
+                e = launch_attn9_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), normtab, win, version == 9, nullptr,
+                                     poly, prop.multiProcessorCount, st);
+            }
+            cudaStreamSynchronize(st);
+            cudaFree(normtab); cudaFree(win);
+        }
+        else if (version == 8) e = launch_attn8_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, prop.multiProcessorCount, st);
         else if (version == 7) e = launch_attn7_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, st);
         else if (version == 6) e = launch_attn6_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, prop.multiProcessorCount, st);
         else if (version == 5) e = launch_attn5_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, st);

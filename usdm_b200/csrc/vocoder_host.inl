@@ -324,15 +324,15 @@ extern "C" int tvb_voc_finalize_weights(tvb_voc_handle* h) {
     CK(cudaDeviceSynchronize());
     voc_free_bag(h->raw_owned);          // the state-dict copies are not needed once packed
     h->raw.clear();
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (!attr.done()) {
         CK(cudaFuncSetAttribute(voc_conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, VcCfg<256>::kSmem));
         CK(cudaFuncSetAttribute(voc_conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, VcCfg<128>::kSmem));
         CK(cudaFuncSetAttribute(voc_conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, VcCfg<64>::kSmem));
         CK(cudaFuncSetAttribute(voc_conv_halo_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, VhCfg<256>::kSmem));
         CK(cudaFuncSetAttribute(voc_conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, VhCfg<128>::kSmem));
         CK(cudaFuncSetAttribute(voc_conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, VhCfg<64>::kSmem));
-        attr = true;
+        attr.mark();
     }
     h->finalized = true;
     return TVB_OK;

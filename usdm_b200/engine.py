@@ -49,6 +49,7 @@ _SIGNATURES = {
     "tvb_process_unit": (C.c_int, [C.c_int, _P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
     "tvb_mel_spectrogram": (C.c_int, [C.c_int, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, C.c_float, C.c_float, _P, C.c_int64, _P]),
     "tvb_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "tvb_async_status": (C.c_int, [_P]),
     "tvb_kernel_launches": (C.c_int64, [_P]),
     "tvb_device_bytes": (C.c_int64, [_P]),
     "tvb_debug_gemm_bf16": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),

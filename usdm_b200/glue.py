@@ -1,6 +1,6 @@
 """Decoder glue around the sampler: the host-side mirror of reference
 src/decoder/voicebox/util/model_util.py — `process_unit` (:50-54), `get_mel` (:24-38), and the mel-producing part of
-`reconstruct_speech` (:72-103; the vocoder call at :104 is out of scope).  The arithmetic runs in libtvb.so
+`reconstruct_speech` (:72-103; the vocoder call at :104 goes to usdm_b200.vocoder).  The arithmetic runs in libtvb.so
 (usdm_b200/csrc/glue.cuh); this module only computes constants (the Slaney mel filterbank) and moves pointers.
 """
 from __future__ import annotations
@@ -104,16 +104,31 @@ def mel_spectrogram(audio: torch.Tensor, hps=DEFAULT_HPS, device="cuda", normali
 
 
 def load_wav(path: str):
-    """Minimal stand-in for train_util.load_wav_to_torch (torchaudio.load is unusable without torchcodec): PCM/float wav via scipy."""
+    """Stand-in for train_util.load_wav_to_torch (:36-38; torchaudio.load is unusable without torchcodec).  torchaudio.load
+    returns float32 in [-1, 1] whatever the file's sample format (normalize=True), so PCM data is scaled here by its own full
+    scale: int16 / 2**15, int32 (and 24-bit, which scipy widens to int32 left-justified) / 2**31, uint8 (offset binary)
+    (x - 128) / 2**7; float files pass through.  Returns (float32 tensor [n] of the first channel, sample rate)."""
     from scipy.io import wavfile
     sr, data = wavfile.read(path)
     if data.ndim > 1:
         data = data[:, 0]
+    if data.dtype == np.int16:
+        data = data.astype(np.float32) / 32768.0
+    elif data.dtype == np.int32:
+        data = (data.astype(np.float64) / 2147483648.0).astype(np.float32)
+    elif data.dtype == np.uint8:
+        data = (data.astype(np.float32) - 128.0) / 128.0
+    elif data.dtype.kind == "f":
+        data = data.astype(np.float32)
+    else:
+        raise ValueError(f"{path}: unsupported wav sample format {data.dtype}")
     return torch.from_numpy(np.ascontiguousarray(data)), sr
 
 
 def get_mel(filepath_or_audio, length: Optional[int] = None, hps=DEFAULT_HPS, device="cuda", normalize: bool = False) -> torch.Tensor:
-    """model_util.py:24-38 (resampling is not provided: the file must already be at hps.sampling_rate)."""
+    """model_util.py:24-38 (resampling is not provided: the file must already be at hps.sampling_rate).  A file always takes the
+    reference's float branch (`audio.clamp(-1, 1)`, :33): its loader hands out floats.  The dither branch of :33
+    (`(audio + rand) / 32768`) is only reachable with an integer tensor, which only a caller passing raw int16 PCM produces."""
     if isinstance(filepath_or_audio, str):
         audio, sr = load_wav(filepath_or_audio)
         if sr != hps.sampling_rate:
@@ -125,8 +140,20 @@ def get_mel(filepath_or_audio, length: Optional[int] = None, hps=DEFAULT_HPS, de
     if audio.dtype.is_floating_point:
         audio = audio.float().clamp(-1, 1)
     else:
-        audio = (audio.float() + torch.rand(audio.shape)) / 32768.0        # model_util.py:33 (dither for integer PCM)
+        audio = (audio.float() + torch.rand(audio.shape)) / 32768.0        # model_util.py:33 (dither for raw integer PCM)
     return mel_spectrogram(audio, hps, device, normalize=normalize)
+
+
+def _hps_of(vocoder, hps):
+    """The reference reads every audio parameter from `vocoder.h` (model_util.py:73-81).  BigVGAN's own config carries
+    sampling_rate / hop_size / num_mels (and n_fft / win_size / fmin / fmax when it was loaded from the published config.json);
+    whatever it does not name falls back to `hps`."""
+    h = getattr(vocoder, "h", None)
+    if h is None:
+        return hps
+    get = h.get if hasattr(h, "get") else (lambda k, d=None: getattr(h, k, d))
+    pick = lambda k: getattr(hps, k) if get(k, None) is None else get(k)
+    return SimpleNamespace(**{k: pick(k) for k in ("sampling_rate", "n_fft", "hop_size", "win_size", "num_mels", "fmin", "fmax")})
 
 
 @torch.inference_mode()
@@ -158,7 +185,9 @@ def reconstruct_mel(agent_unit, voicebox, reference_audio=None, reference_unit=N
 def reconstruct_speech(agent_unit, voicebox, vocoder, reference_audio=None, reference_unit=None, n_timesteps: int = 50, hps=DEFAULT_HPS,
                        device="cuda", solver: str = "heun", gradient_scale: float = 1.0):
     """reconstruct_speech (model_util.py:72-105) end to end on the B200: units -> mel (usdm_b200.Voicebox) -> waveform
-    (usdm_b200.vocoder.BigVGAN), returned like the reference as a clamped float32 numpy array [T_agent * hop]."""
+    (usdm_b200.vocoder.BigVGAN), returned like the reference as a clamped float32 numpy array [T_agent * hop].  Like the
+    reference (`process_unit(agent_unit, vocoder.h, device)`, :73) the audio parameters come from `vocoder.h`."""
+    hps = _hps_of(vocoder, hps)
     y_dec = reconstruct_mel(agent_unit, voicebox, reference_audio, reference_unit, n_timesteps, hps, device, solver, gradient_scale)
     return vocoder.forward(y_dec).cpu().squeeze().clamp(-1, 1).numpy()          # model_util.py:104
 

@@ -32,7 +32,22 @@ BIGVGAN_22K_80 = dict(
     num_mels=80, upsample_rates=[4, 4, 2, 2, 2, 2], upsample_kernel_sizes=[8, 8, 4, 4, 4, 4], upsample_initial_channel=1536,
     resblock="1", resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]],
     activation="snakebeta", snake_logscale=True, sampling_rate=22050, hop_size=256,
+    # the audio front-end entries of the same config.json, which get_mel reads through `vocoder.h` (model_util.py:35-36)
+    n_fft=1024, win_size=1024, fmin=0, fmax=8000,
 )
+
+
+class AttrDict(dict):
+    """The reference's `vocoder.h` (vocoder/env.py:8-11): a dict whose keys also read and write as attributes."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k) from None
+
+    def __setattr__(self, k, v):
+        self[k] = v
 
 
 def kaiser_sinc_filter(cutoff: float = 0.25, half_width: float = 0.3, kernel_size: int = 12) -> torch.Tensor:
@@ -96,7 +111,7 @@ class BigVGAN(nn.Module, PyTorchModelHubMixin):
     def __init__(self, h: Optional[dict] = None, use_cuda_kernel: bool = False):
         super().__init__()
         h = dict(h or BIGVGAN_22K_80)
-        self.h = h
+        self.h = AttrDict(h)                 # reference callers use attribute access (`vocoder.h.num_mels`, model_util.py:73-84)
         if str(h.get("resblock", "1")) != "1":
             raise NotImplementedError("only resblock '1' (AMPBlock1) is implemented: it is what bigvgan_22khz_80band ships")
         if h["activation"] not in ("snake", "snakebeta"):
@@ -259,7 +274,7 @@ class BigVGAN(nn.Module, PyTorchModelHubMixin):
     def _save_pretrained(self, save_directory) -> None:
         torch.save({"generator": self.state_dict()}, os.path.join(str(save_directory), "bigvgan_generator.pt"))
         with open(os.path.join(str(save_directory), "config.json"), "w") as f:
-            json.dump(self.h, f, indent=4)
+            json.dump(dict(self.h), f, indent=4)
 
     @classmethod
     def _from_pretrained(cls, *, model_id, revision=None, cache_dir=None, force_download=False, proxies=None, resume_download=None,

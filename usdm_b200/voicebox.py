@@ -319,6 +319,13 @@ class Voicebox(nn.Module, PyTorchModelHubMixin):
         u = u * loss_mask
         return torch.nn.functional.mse_loss(ue, u, reduction="sum") / (torch.sum(loss_mask) * u.shape[1])
 
+    def check_async(self) -> None:
+        """Raise ValueError if a kernel of an earlier (completed) call met unit ids outside [0, n_tokens] - the asynchronous
+        counterpart of the device-side assert of the reference's nn.Embedding (networks.py:305).  The same check runs at the
+        start of every sampling call; this one does not synchronise (synchronise the stream first to cover the last call)."""
+        if self._handle is not None:
+            E.check(E.load_library().tvb_async_status(self._handle))
+
     # ---- stats ---------------------------------------------------------------------------------------------
     def kernel_launches(self) -> int:
         return 0 if self._handle is None else int(E.load_library().tvb_kernel_launches(self._handle))
