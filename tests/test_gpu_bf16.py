@@ -33,6 +33,7 @@ ABLATIONS = [
     dict(ln_fuse=2), dict(ln_fuse=2, attn_tc=0, conv_tc=0),    # LayerNorm inside the residual GEMM epilogue (8-CTA clusters, DSMEM)
     dict(ln_fuse=1), dict(ln_fuse=0), dict(ln1_fold=0), dict(ln1_fold=0, zigzag=0), dict(pdl=0),
     dict(gemm_bn=0), dict(gemm_bn=0, ln1_fold=0), dict(gemm_bn=1, ln1_fold=0),   # 256-column GEMM tiles at small M (the default there is 128)
+    dict(resid_l2=1), dict(resid_l2=2),                       # residual chunks pulled into the L2 ahead of their staged load
     dict(),                                                  # shipping defaults
 ]
 

@@ -1,0 +1,174 @@
+// Attention kernel laboratory (diagnostics, not part of libtvb.so): times attn9_tc.cuh / attn8_tc.cuh on synthetic q|k|v rows of the
+// configs[1] shape with CUDA events, including the LAB timing ablations of attn9 (pieces of the softmax body switched off).
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o tools/attn_lab tools/attn_lab.cu && ./tools/attn_lab [scale] [len] [nseq]
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#define A9_LAB_TRACE
+#include "../usdm_b200/csrc/attn9_tc.cuh"
+
+using namespace tvb;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+typedef CUresult (*PFN_encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+__global__ void k_init(__nv_bfloat16* qkv, size_t n, int H, float scale, unsigned seed) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned x = (unsigned)(i * 2654435761u) ^ seed;
+        x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+        unsigned y = x * 1664525u + 1013904223u;
+        const float u1 = ((x >> 8) + 1) * (1.0f / 16777217.0f), u2 = (y >> 8) * (1.0f / 16777216.0f);
+        float v = sqrtf(-2.0f * logf(u1)) * cosf(6.2831853f * u2) * scale;
+        if ((int)(i % (3 * H)) < H) v *= 0.125f * 1.4426950408889634f;
+        qkv[i] = __float2bfloat16_rn(v);
+    }
+}
+
+template <typename F>
+static float time_ms(F&& fn, int iters) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) fn();
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < iters; ++i) fn();
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    return ms / iters;
+}
+
+int main(int argc, char** argv) {
+    const float scale = argc > 1 ? atof(argv[1]) : 0.45f;
+    const int len = argc > 2 ? atoi(argv[2]) : 1134;
+    const int nseq = argc > 3 ? atoi(argv[3]) : 32;
+    const int H = 1024, nh = 16;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    const int sms = prop.multiProcessorCount;
+    std::vector<int4> work;
+    int o = 0;
+    for (int s = 0; s < nseq; ++s) {
+        for (int q0 = 0; q0 < len; q0 += ATT_BQ) work.push_back(make_int4(s, q0, o, len));
+        o += len + 16;
+    }
+    const int rows = (o + 255) / 256 * 256;
+    std::stable_sort(work.begin(), work.end(), [](const int4& a, const int4& b) {
+        auto cost = [](const int4& w) { return ((w.w + ATT_BK - 1) / ATT_BK) * (w.y + 128 < w.w ? 2 : 1); };
+        return cost(a) > cost(b);
+    });
+    __nv_bfloat16 *qkv, *ctx;
+    CK(cudaMalloc(&qkv, (size_t)rows * 3 * H * 2));
+    CK(cudaMalloc(&ctx, (size_t)rows * H * 2));
+    k_init<<<148 * 8, 256>>>(qkv, (size_t)rows * 3 * H, H, scale, 12345u);
+    CK(cudaGetLastError());
+    int4 *d_work, *d_win;
+    CK(cudaMalloc(&d_work, work.size() * sizeof(int4)));
+    CK(cudaMalloc(&d_win, work.size() * nh * sizeof(int4)));
+    CK(cudaMemcpy(d_work, work.data(), work.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    float *normtab, *slopes;
+    CK(cudaMalloc(&normtab, (size_t)(rows / 32 + 1) * 2 * nh * sizeof(float)));
+    std::vector<float> sl(nh);
+    for (int i = 0; i < nh; ++i) sl[i] = powf(2.0f, -0.5f * (i + 1));
+    CK(cudaMalloc(&slopes, nh * sizeof(float)));
+    CK(cudaMemcpy(slopes, sl.data(), nh * sizeof(float), cudaMemcpyHostToDevice));
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    CUtensorMap tm;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)(3 * H), (cuuint64_t)rows};
+        cuuint64_t strides[1] = {(cuuint64_t)(3 * H) * 2};
+        cuuint32_t box[2] = {64, 128};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = ((PFN_encode)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { printf("tensor map failed %d\n", (int)r); return 1; }
+    }
+    const int nwork = (int)work.size(), n_items = nwork * nh;
+    k_attn9_rownorm<<<(rows + 31) / 32, 256>>>(qkv, rows, H, nh, normtab);
+    CK(cudaDeviceSynchronize());
+    const double flops = 4.0 * 64 * nh * (double)nseq * len * len;
+    printf("# attn_lab: %d sequences x %d tokens, %d heads, scale %.2f, %d items, %d SMs\n", nseq, len, nh, scale, n_items, sms);
+    for (int use_win = 0; use_win < 2; ++use_win) {
+        k_attn9_plan<<<(n_items + 7) / 8, 256>>>(d_work, n_items, nh, slopes, normtab, use_win, d_win, nullptr);
+        CK(cudaDeviceSynchronize());
+        std::vector<int4> win(n_items);
+        CK(cudaMemcpy(win.data(), d_win, n_items * sizeof(int4), cudaMemcpyDeviceToHost));
+        long blocks = 0, full = 0;
+        float shift_max = 0;
+        for (int t = 0; t < n_items; ++t) {
+            const int4 w = work[t / nh];
+            const int nkb = (w.w + ATT_BK - 1) / ATT_BK, nhv = (w.y + 128 < w.w) ? 2 : 1;
+            const int lo[2] = {win[t].x & 0xffff, win[t].y & 0xffff}, hi[2] = {win[t].x >> 16, win[t].y >> 16};
+            for (int h = 0; h < nhv; ++h) { blocks += 1 + (hi[h] >= lo[h] ? hi[h] - lo[h] + 1 : 0); full += nkb; }
+            float sh; memcpy(&sh, &win[t].z, 4); shift_max = std::max(shift_max, sh);
+        }
+        printf("window=%d: %ld of %ld block-halves kept (%.1f %%), max shift %.1f\n", use_win, blocks, full, 100.0 * blocks / full, shift_max);
+#define RUN9(POLY, LAB, name)                                                                                                     \
+        {                                                                                                                         \
+            const float ms = time_ms([&] { CK((launch_attn9_t<POLY, LAB>(tm, ctx, H, nh, slopes, d_work, d_win, nwork, sms, 0, false))); }, 20); \
+            printf("  v9 win=%d poly=%d lab=%2d %-34s %8.1f us  %7.1f TFLOP/s (algorithmic)  %6.0f cycles/block-half @1.9GHz\n", use_win, POLY, LAB, name, ms * 1e3, \
+                   flops / (ms * 1e-3) / 1e12, ms * 1e-3 * 1.9e9 * sms / blocks);                                                 \
+        }
+        RUN9(3, 0, "baseline");
+        RUN9(0, 0, "all exp2 on MUFU");
+        RUN9(2, 0, "poly 1/2");
+        RUN9(4, 0, "poly 1/4");
+        if (use_win == 0) {
+            RUN9(3, 1, "no exponential");
+            RUN9(3, 2, "no row sum");
+            RUN9(3, 4, "no offset add");
+            RUN9(3, 8, "no bf16 pack");
+            RUN9(3, 16, "no PV wait before P store");
+            RUN9(3, 3, "no exp, no row sum");
+            RUN9(3, 7, "no exp / sum / offset");
+            RUN9(3, 15, "no exp / sum / offset / pack");
+            RUN9(0, 15, "same, poly 0");
+            RUN9(0, 1, "poly 0, no exponential");
+        }
+    }
+    // ---- event trace of CTA 0 (LAB bit 5): per role (softmax half A / B quad 0, PV issuer, QK issuer) tagged clock64() stamps
+    for (int lab : {32, 32 + 15}) {
+        long long* d_tr;
+        CK(cudaMalloc(&d_tr, 4 * 1024 * sizeof(long long)));
+        CK(cudaMemset(d_tr, 0, 4 * 1024 * sizeof(long long)));
+        CK(cudaMemcpyToSymbol(g_a9_trace, &d_tr, sizeof(d_tr)));
+        k_attn9_plan<<<(n_items + 7) / 8, 256>>>(d_work, n_items, nh, slopes, normtab, 0, d_win, nullptr);
+        if (lab == 32) CK((launch_attn9_t<3, 32>(tm, ctx, H, nh, slopes, d_work, d_win, nwork, sms, 0, false)));
+        else CK((launch_attn9_t<3, 47>(tm, ctx, H, nh, slopes, d_work, d_win, nwork, sms, 0, false)));
+        CK(cudaDeviceSynchronize());
+        std::vector<long long> tr(4 * 1024);
+        CK(cudaMemcpy(tr.data(), d_tr, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        struct Ev { long long t; int role, tag; };
+        std::vector<Ev> ev;
+        for (int r = 0; r < 4; ++r)
+            for (int i = 0; i < 1024; ++i)
+                if (tr[r * 1024 + i]) ev.push_back({tr[r * 1024 + i] & 0xffffffffffffll, r, (int)(tr[r * 1024 + i] >> 48)});
+        std::sort(ev.begin(), ev.end(), [](const Ev& a, const Ev& b) { return a.t < b.t; });
+        printf("# trace lab=%d (CTA 0; roles: 0/1 softmax half A/B warp 0, 2 PV issuer, 3 QK issuer; softmax tags: 1 scores seen, 2-5 chunk 0-3 in registers "
+               "(5 = S released), 6 math done, 7 PV wait done, 8 P handed over; PV: 20+h p_ready seen, 22+h issued; QK: 30+h s_free seen, 32+h issued)\n", lab);
+        const long long t0 = ev.empty() ? 0 : ev[0].t;
+        int shown = 0;
+        for (const Ev& e : ev) {
+            if (e.t - t0 < 40000) continue;                     // skip the first item: steady state
+            printf("  %8lld role %d tag %2d\n", e.t - t0, e.role, e.tag);
+            if (++shown >= 150) break;
+        }
+        cudaFree(d_tr);
+    }
+    {
+        const float ms = time_ms([&] { CK(launch_attn8_raw(tm, ctx, H, nh, slopes, d_work, nwork, 3, sms, 0, false, false)); }, 20);
+        printf("  v8 poly=3 %-45s %8.1f us  %7.1f TFLOP/s\n", "", ms * 1e3, flops / (ms * 1e-3) / 1e12);
+    }
+    return 0;
+}

@@ -159,7 +159,22 @@ __global__ void __launch_bounds__(256) k_attn9_plan(const int4* __restrict__ wor
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
-template <int POLY>
+// Event trace for tools/attn_lab.cu (compiled in only there): CTA 0 stamps (tag << 48 | clock) per role into g_a9_trace[role][1024].
+#ifdef A9_LAB_TRACE
+__device__ long long* g_a9_trace;
+#define A9_STAMP(role, tag)                                                                                                  \
+    do {                                                                                                                     \
+        if ((LAB & 32) && blockIdx.x == 0 && lane == 0 && tr_n < 1024)                                                       \
+            g_a9_trace[(role) * 1024 + tr_n++] = (static_cast<long long>(tag) << 48) | (clock64() & 0xffffffffffffll);       \
+    } while (0)
+#else
+#define A9_STAMP(role, tag) do { } while (0)
+#endif
+
+// LAB (tools/attn_lab.cu only; the library always instantiates LAB = 0): timing ablations that switch pieces of the softmax body
+// off -- bit 0: no exponential, bit 1: no row sum, bit 2: no offset add, bit 3: no bf16 pack, bit 4: the P hand-over does not wait for
+// the previous PV.  Results are meaningless with LAB != 0.
+template <int POLY, int LAB = 0>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn9_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ ctx, int H, int nheads,
              const float* __restrict__ slopes, const int4* __restrict__ work, const int4* __restrict__ win, int n_items) {
@@ -180,6 +195,7 @@ attn9_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
 
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x;
+    [[maybe_unused]] int tr_n = 0;
 
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();   // swizzle-128B tiles need 1024-B alignment
     if (warp_idx == 0 && lane == 0) tma_prefetch_desc(&tmQKV);
@@ -282,6 +298,7 @@ attn9_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                     if (half >= w.nh || !a9_needed(w, half, j)) continue;
                     const int c = pvc[half]++;
                     mbar_wait(&p_ready[half], c & 1);
+                    A9_STAMP(2, 20 + half);
                     if (jj == 0) {                                                        // this PV overwrites O: the previous item's
                         if (cnt[half] > 0) mbar_wait(&o_free[half], (cnt[half] - 1) & 1); // epilogue must have read it out
                         ++cnt[half];
@@ -298,6 +315,7 @@ attn9_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                         if (half == last_half) umma_commit(&kv_empty[slot]);              // every MMA reading this stage has been issued
                     }
                     __syncwarp();
+                    A9_STAMP(2, 22 + half);
                 }
                 if (++slot == A4_KV_STAGES) slot = 0;
             }
@@ -330,6 +348,7 @@ attn9_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                     if (half >= w.nh || !a9_needed(w, half, j)) continue;
                     const int c = qkc[half]++;
                     mbar_wait(&s_free[half], (c & 1) ^ 1);  // block c - 1 of this half is in its threads' registers (fresh barrier: passes)
+                    A9_STAMP(3, 30 + half);
                     tc_fence_after();
                     const uint32_t d = tmem_base + half * 128;
                     const uint64_t da = dq0 + static_cast<uint64_t>((qb * 2 + half) * (ATT_TILE_BYTES >> 4));
@@ -347,6 +366,7 @@ attn9_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                         }
                     }
                     __syncwarp();
+                    A9_STAMP(3, 32 + half);
                 }
                 if (++slot == A4_KV_STAGES) { slot = 0; kvpar ^= 1; }
             }
@@ -407,6 +427,7 @@ attn9_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                     // additive term of this block: per-row constant (off-diagonal; the key-dependent part came out of the MMA) or none
                     const float c_row = diag ? 0.f : -slope2 * fabsf(static_cast<float>(i - k0));
                     tmem_ld_wait_dep(ca);                    // chunk 0 (requested when the block's scores arrived)
+                    if (quad == 0) A9_STAMP(half, 2);
                     if (GEN && j == 0) m_ref = __uint_as_float(ca[0]) + w.shift;        // key 0: the time token, bias 0
                     tmem_ld_32x32(tmem_S + 32, cb);
                     const float off = c_row - m_ref;
@@ -435,32 +456,38 @@ attn9_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                         }
 #pragma unroll
                         for (int u = 0; u < 16; ++u) {
-                            const uint64_t x2 = fadd2(pack2f(__uint_as_float(cur[2 * u]), __uint_as_float(cur[2 * u + 1])), off2);
+                            uint64_t x2 = pack2f(__uint_as_float(cur[2 * u]), __uint_as_float(cur[2 * u + 1]));
+                            if (!(LAB & 4)) x2 = fadd2(x2, off2);
                             uint64_t p2;
                             if (POLY > 0 && (u % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) {
-                                p2 = exp2_poly2(x2);
-                                accp2 = fadd2(accp2, p2);
+                                p2 = (LAB & 1) ? x2 : exp2_poly2(x2);
+                                if (!(LAB & 2)) accp2 = fadd2(accp2, p2);
                             } else {
                                 float lo, hi;
                                 unpack2f(x2, lo, hi);
-                                lo = ex2_approx(lo);
-                                hi = ex2_approx(hi);
+                                if (!(LAB & 1)) {
+                                    lo = ex2_approx(lo);
+                                    hi = ex2_approx(hi);
+                                }
                                 p2 = pack2f(lo, hi);
-                                acc2 = fadd2(acc2, p2);
+                                if (!(LAB & 2)) acc2 = fadd2(acc2, p2);
                             }
                             float lo, hi;
                             unpack2f(p2, lo, hi);
-                            s[c * 16 + u] = pack_bf16x2(lo, hi);
+                            s[c * 16 + u] = (LAB & 8) ? __float_as_uint(lo) ^ __float_as_uint(hi) : pack_bf16x2(lo, hi);
                         }
                     };
                     proc(ca, 0);
                     tmem_ld_wait_dep(cb);
+                    if (quad == 0) A9_STAMP(half, 3);
                     tmem_ld_32x32(tmem_S + 64, ca);
                     proc(cb, 1);
                     tmem_ld_wait_dep(ca);
+                    if (quad == 0) A9_STAMP(half, 4);
                     tmem_ld_32x32(tmem_S + 96, cb);
                     proc(ca, 2);
                     tmem_ld_wait_dep(cb);
+                    if (quad == 0) A9_STAMP(half, 5);
                     // the whole block is in registers: hand S back, the next QK^T overlaps the last chunk and the P hand-over
                     tc_fence_before();
                     mbar_arrive(&s_free[half]);
@@ -471,17 +498,21 @@ attn9_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
                 };
                 if (j != 0 && j != jd && k0 + ATT_BK <= len) body(std::false_type{});
                 else body(std::true_type{});
+                if (quad == 0) A9_STAMP(half, 6);
                 // ---- P_half must have been read by the previous PV of this half before it is overwritten
-                if (cblk > 0) wait_pv(cblk - 1);
+                if (cblk > 0 && !(LAB & 16)) wait_pv(cblk - 1);
                 tc_fence_after();
+                if (quad == 0) A9_STAMP(half, 7);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) tmem_st_32x16(tmem_P + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&s[c * 16]));
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&p_ready[half]);
+                if (quad == 0) A9_STAMP(half, 8);
                 ++cblk;
                 if (more) {                                  // scores of the half's next block: wait, then request their first 32 columns
                     mbar_wait(&s_full[half], cblk & 1);
+                    if (quad == 0) A9_STAMP(half, 1);
                     tc_fence_after();
                     tmem_ld_32x32(tmem_S, ca);
                     jnext = a9_block(w, jj2);
@@ -497,7 +528,7 @@ attn9_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&o_free[half]);
-            const float inv = 1.0f / l_run;
+            const float inv = 1.0f / ((LAB & 2) ? 1.0f : l_run);
             if (i < len) {
                 __nv_bfloat16* dst = ctx + static_cast<size_t>(w.start + i) * H + w.head * ATT_D;
 #pragma unroll
@@ -518,12 +549,12 @@ attn9_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
     }
 }
 
-template <int POLY>
+template <int POLY, int LAB = 0>
 inline cudaError_t launch_attn9_t(const CUtensorMap& tmQKV, __nv_bfloat16* ctx, int H, int nheads, const float* slopes, const int4* work,
                                   const int4* win, int nwork, int num_sms, cudaStream_t st, bool pdl) {
     static PerDeviceOnce attr;
     if (!attr.done()) {
-        cudaError_t e = cudaFuncSetAttribute(attn9_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, A9_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(attn9_kernel<POLY, LAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, A9_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr.mark();
     }
@@ -535,7 +566,7 @@ inline cudaError_t launch_attn9_t(const CUtensorMap& tmQKV, __nv_bfloat16* ctx, 
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, attn9_kernel<POLY>, tmQKV, ctx, H, nheads, slopes, work, win, n_items);
+    return cudaLaunchKernelEx(&cfg, attn9_kernel<POLY, LAB>, tmQKV, ctx, H, nheads, slopes, work, win, n_items);
 }
 // The q columns of tmQKV must have been produced with W_q, b_q scaled by head_dim^-0.5 * log2(e); normtab holds the row-block norms of
 // the same rows (QKV GEMM epilogue or k_attn9_rownorm); win is scratch for nwork * nheads int4.

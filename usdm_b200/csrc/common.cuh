@@ -117,6 +117,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// Pull a 2-D box into the L2 only (no shared-memory destination, no completion to wait for): a later TMA load of the same box then
+// sees L2 latency instead of HBM latency under load.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int32_t c_inner, int32_t c_outer) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c_inner),
+                 "r"(c_outer)
+                 : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA issue, commit, TMEM loads
 // ------------------------------------------------------------------------------------------

@@ -61,6 +61,10 @@ struct GemmParams {
     float* rownorm;           // EPI_BF16, CTA-pair kernels: when set, normtab[row / 32][col / 64] = max over the 32 rows of the squared norm of the 64
     int rownorm_cols;         //   output columns (fp32 values before the bf16 rounding), for columns < rownorm_cols: the |q|, |k| row-block maxima
     int rownorm_ld;           //   the attention kernel bounds its logits with (attn9_tc.cuh); row stride rownorm_ld
+    int resid_l2;             // CTA-pair residual epilogues (ablation, default 0): 1 = every epilogue warp pulls the residual chunks of its NEXT tile into
+                              // the L2 one tile ahead (cp.async.bulk.prefetch.tensor), 2 = the chunk after the next one (the staged TMA load itself runs
+                              // one chunk ahead).  Measured (profiles/r02): 1 costs the attention-out GEMM 7 % and FFN-out 4 % -- the kernel is HBM
+                              // bandwidth bound (452 MB per 77 GFLOP launch), not latency bound, and the early lines are evicted before they are used
     int reverse;              // CTA-pair kernels: walk the 256-row blocks from the last to the first.  Consumers traverse opposite to
                               // the kernel that produced their input, so the rows they read first are the ones still in the 126 MB L2.
 };
@@ -410,17 +414,31 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
             row = tile_m0(tile) + static_cast<int>(cta) * 128 + quad * 32;
             col = (tile % tiles_n) * BN + chalf * kHalf + c * kChunkCols;
         };
+        auto prefetch_tile_resid = [&](int tile) {                // one lane: this warp's residual chunks of `tile` into the L2
+            if (tile < num_tiles) {
+#pragma unroll
+                for (int c = 0; c < kChunks; ++c) {
+                    int col, row;
+                    chunk_coords(tile, c, col, row);
+                    tma_prefetch_l2_2d(&tm.resid, col, row);
+                }
+            }
+        };
         if constexpr (kResid) {
             if (lane == 0 && cluster_id < num_tiles) {
                 int col, row;
                 chunk_coords(cluster_id, 0, col, row);
                 mbar_arrive_expect_tx(&rb[0], G2_EPI_TILE);
                 tma_load_2d(stg, &tm.resid, &rb[0], col, row);
+                if (p.resid_l2 == 1) prefetch_tile_resid(cluster_id);
             }
         }
         int it = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
             const int as = it & 1;
+            if constexpr (kResid) {
+                if (p.resid_l2 == 1 && lane == 0) prefetch_tile_resid(tile + num_clusters);
+            }
             float fa = 1.f, fb = 0.f;                                 // FOLD: rstd and -rstd * mean of this thread's row
             if constexpr (EPI == EPI_FOLD_GELU) {
                 // before the accumulator wait: the partials of the row come through an L2 that the operand ring keeps saturated,
@@ -476,6 +494,15 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                             chunk_coords(nt, nc, ncol, nrow);
                             mbar_arrive_expect_tx(&rb[nbuf], G2_EPI_TILE);
                             tma_load_2d(stg + nbuf * G2_EPI_TILE, &tm.resid, &rb[nbuf], ncol, nrow);
+                        }
+                        if (p.resid_l2 == 2) {
+                            int ft = tile, fc = c + 2;
+                            if (fc >= kChunks) { fc -= kChunks; ft = tile + num_clusters; }
+                            if (ft < num_tiles) {
+                                int fcol, frow;
+                                chunk_coords(ft, fc, fcol, frow);
+                                tma_prefetch_l2_2d(&tm.resid, fcol, frow);
+                            }
                         }
                     } else {
                         tma_store_wait_read<G2_EPI_BUFS - 1>();   // the store issued G2_EPI_BUFS chunks ago (same buffer) is done reading
