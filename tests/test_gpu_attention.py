@@ -71,7 +71,7 @@ def _run(lens, version, poly, seed=0, scale=1.0, spikes=(), return_ctx=False):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("version,poly", [(9, 0), (9, 2), (9, 3), (9, 4), (90, 3), (8, 0), (8, 2), (8, 3), (8, 4), (7, 0), (7, 2), (7, 3), (7, 4), (6, 0), (6, 2), (6, 3), (6, 4), (5, 0), (5, 2), (5, 3), (5, 4), (4, 0), (4, 2), (4, 3), (4, 4), (3, 0), (2, 0)])
+@pytest.mark.parametrize("version,poly", [(10, 0), (10, 2), (10, 3), (10, 4), (100, 4), (9, 0), (9, 2), (9, 3), (9, 4), (90, 3), (8, 0), (8, 2), (8, 3), (8, 4), (7, 0), (7, 2), (7, 3), (7, 4), (6, 0), (6, 2), (6, 3), (6, 4), (5, 0), (5, 2), (5, 3), (5, 4), (4, 0), (4, 2), (4, 3), (4, 4), (3, 0), (2, 0)])
 def test_attention_kernel_vs_fp32_math(version, poly):
     # lengths cover: 1 key, < 1 block, exact block multiples, odd tails, one / two query halves, the configs[1] length
     lens = [1134, 1, 127, 128, 129, 256, 257, 384, 700, 389, 2, 513]
@@ -104,7 +104,7 @@ def test_attention_v8_single_key_spike_beyond_the_polynomial_range(poly):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("version", [4, 5, 6, 7, 8, 9, 90])
+@pytest.mark.parametrize("version", [4, 5, 6, 7, 8, 9, 90, 10, 100])
 def test_attention_long_form(version):
     """configs[2]-like length (30 s + prompt): 23 key blocks, 12 query tiles per head."""
     rel, mx = _run([2856, 2584], version, 0, seed=2)
@@ -113,7 +113,7 @@ def test_attention_long_form(version):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("version", [6, 8, 9])
+@pytest.mark.parametrize("version", [6, 8, 9, 10])
 def test_attention_persistent_many_items_per_cta(version):
     """More work items than SMs and very uneven ones (1-key, one-half, two-half tiles interleaved), so that every CTA of the
     persistent kernel crosses several item boundaries with different half counts and heads."""
@@ -126,28 +126,30 @@ def test_attention_persistent_many_items_per_cta(version):
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("poly", [0, 3])
 @pytest.mark.parametrize("scale", [0.3, 1.0, 2.0])
-def test_attention_v9_fixed_reference_and_window(poly, scale):
+@pytest.mark.parametrize("v", [9, 10])
+def test_attention_v9_fixed_reference_and_window(v, poly, scale):
     """attn9_tc.cuh: (a) the fixed softmax reference s(i, key 0) + shift: scale 2.0 gives a logit bound 2 max|q| max|k| ~ 160 in
     the log2 domain, i.e. a non-zero shift, scale 0.3 a bound of a few units; (b) the ALiBi window (version 9) against the same kernel
     with every key block processed (version 90): skipped keys are below 2^-40 of their row sum, so the two may differ by an odd
     last-place rounding at most."""
     lens = [1134, 700, 2856, 129, 513, 300]
-    rel_w, ctx_w = _run(lens, 9, poly, seed=7, scale=scale, return_ctx=True)
-    rel_f, ctx_f = _run(lens, 90, poly, seed=7, scale=scale, return_ctx=True)
+    rel_w, ctx_w = _run(lens, v, poly, seed=7, scale=scale, return_ctx=True)
+    rel_f, ctx_f = _run(lens, 10 * v, poly, seed=7, scale=scale, return_ctx=True)
     diff = (ctx_w.float() - ctx_f.float()).abs()
     changed = int((diff > 0).sum())
-    print(f"attention v9 poly={poly} scale={scale}: rel-L2 window {rel_w:.3e} / full {rel_f:.3e}; elements that differ between the two: {changed} of {diff.numel()}, max {float(diff.max()):.3e}")
+    print(f"attention v{v} poly={poly} scale={scale}: rel-L2 window {rel_w:.3e} / full {rel_f:.3e}; elements that differ between the two: {changed} of {diff.numel()}, max {float(diff.max()):.3e}")
     assert rel_w < 6e-3 and rel_f < 6e-3
     assert changed <= diff.numel() * 1e-4
     assert float((diff / ctx_f.float().abs().clamp_min(1e-3)).max()) < 1e-2          # one bf16 ulp of the output
 
 
 @pytest.mark.timeout(600)
-def test_attention_v9_key0_spike_and_far_key_spike():
+@pytest.mark.parametrize("v", [9, 10])
+def test_attention_v9_key0_spike_and_far_key_spike(v):
     """Scores far from the reference in both directions: a spike ON the time token (every other exponent becomes very negative) and
     a spike on a far key inside the logit bound (exponent close to the top of the range)."""
     lens = [700, 640]
     spikes = [(0, 0, 60.0), (1, 3 * 128 + 37, 60.0)]
-    rel, mx = _run(lens, 9, 3, seed=5, scale=0.3, spikes=spikes)
-    print(f"attention v9 spikes: rel-L2 {rel:.3e}, max-abs {mx:.3e}")
+    rel, mx = _run(lens, v, 3, seed=5, scale=0.3, spikes=spikes)
+    print(f"attention v{v} spikes: rel-L2 {rel:.3e}, max-abs {mx:.3e}")
     assert rel < 6e-3

@@ -28,7 +28,7 @@ ABLATIONS = [
     dict(frame_tc=0, out_tc=0),
     dict(frame_tc=0),                                        # CUDA-core frame projection (the shipping path is a tcgen05 GEMM over hi/lo bf16 planes of y)
     dict(attn_v=3),                                          # previous attention kernel generations
-    dict(attn_v=4), dict(attn_v=5), dict(attn_v=5, attn_poly=3), dict(attn_v=6), dict(attn_v=6, attn_poly=3), dict(attn_v=7), dict(attn_v=7, attn_poly=0), dict(attn_v=8), dict(attn_v=8, attn_poly=0), dict(attn_v=9, attn_win=0), dict(attn_v=9, attn_poly=0), dict(attn_v=9, gemm_2cta=0),
+    dict(attn_v=4), dict(attn_v=5), dict(attn_v=5, attn_poly=3), dict(attn_v=6), dict(attn_v=6, attn_poly=3), dict(attn_v=7), dict(attn_v=7, attn_poly=0), dict(attn_v=8), dict(attn_v=8, attn_poly=0), dict(attn_v=9), dict(attn_v=9, attn_win=0), dict(attn_v=10, attn_win=0), dict(attn_v=10, attn_poly=0), dict(attn_v=9, attn_poly=0), dict(attn_v=9, gemm_2cta=0),
     dict(attn_poly=2), dict(attn_poly=3), dict(attn_poly=4),  # exp2 partly on the FMA pipe
     dict(ln_fuse=2), dict(ln_fuse=2, attn_tc=0, conv_tc=0),    # LayerNorm inside the residual GEMM epilogue (8-CTA clusters, DSMEM)
     dict(ln_fuse=1), dict(ln_fuse=0), dict(ln1_fold=0), dict(ln1_fold=0, zigzag=0), dict(pdl=0),

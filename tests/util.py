@@ -44,7 +44,7 @@ def model(seed=0, perturb=False, precision="bf16"):
     m.set_option("gemm_mc", 0)
     m.set_option("gemm_bn", 1)
     m.set_option("resid_l2", 0)
-    m.set_option("attn_v", 9)
+    m.set_option("attn_v", 10)
     m.set_option("attn_win", 1)
     m.set_option("attn_poly", 4)
     m.set_option("ln_fuse", 1)

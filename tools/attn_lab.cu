@@ -11,7 +11,8 @@
 #include <vector>
 
 #define A9_LAB_TRACE
-#include "../usdm_b200/csrc/attn9_tc.cuh"
+#define A10_LAB_TRACE
+#include "../usdm_b200/csrc/attn10_tc.cuh"
 
 using namespace tvb;
 
@@ -72,6 +73,8 @@ int main(int argc, char** argv) {
     k_init<<<148 * 8, 256>>>(qkv, (size_t)rows * 3 * H, H, scale, 12345u);
     CK(cudaGetLastError());
     int4 *d_work, *d_win;
+    int* d_order;
+    CK(cudaMalloc(&d_order, work.size() * 16 * sizeof(int)));
     CK(cudaMalloc(&d_work, work.size() * sizeof(int4)));
     CK(cudaMalloc(&d_win, work.size() * nh * sizeof(int4)));
     CK(cudaMemcpy(d_work, work.data(), work.size() * sizeof(int4), cudaMemcpyHostToDevice));
@@ -94,12 +97,36 @@ int main(int argc, char** argv) {
                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { printf("tensor map failed %d\n", (int)r); return 1; }
     }
+    // v10: key-position table + its 32-byte-swizzle map
+    __nv_bfloat16* pos;
+    CUtensorMap tmp;
+    {
+        std::vector<int> hs(rows, -1), hp(rows, 0);
+        int oo = 0;
+        for (int s = 0; s < nseq; ++s) { for (int i = 0; i < len; ++i) { hs[oo + i] = s; hp[oo + i] = i; } oo += len + 16; }
+        int *rseq, *rpos;
+        CK(cudaMalloc(&rseq, rows * sizeof(int))); CK(cudaMalloc(&rpos, rows * sizeof(int)));
+        CK(cudaMemcpy(rseq, hs.data(), rows * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(rpos, hp.data(), rows * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&pos, (size_t)rows * 16 * 2));
+        k_attn10_pos<<<(rows + 255) / 256, 256>>>(rseq, rpos, rows, pos);
+        CK(cudaDeviceSynchronize());
+        cuuint64_t dims[2] = {16, (cuuint64_t)rows};
+        cuuint64_t strides[1] = {32};
+        cuuint32_t box[2] = {16, 128};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = ((PFN_encode)fn)(&tmp, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pos, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { printf("pos tensor map failed %d\n", (int)r); return 1; }
+    }
     const int nwork = (int)work.size(), n_items = nwork * nh;
     k_attn9_rownorm<<<(rows + 31) / 32, 256>>>(qkv, rows, H, nh, normtab);
     CK(cudaDeviceSynchronize());
     const double flops = 4.0 * 64 * nh * (double)nseq * len * len;
     printf("# attn_lab: %d sequences x %d tokens, %d heads, scale %.2f, %d items, %d SMs\n", nseq, len, nh, scale, n_items, sms);
+    const int* lab_order = nullptr;
     for (int use_win = 0; use_win < 2; ++use_win) {
+        lab_order = nullptr;
         k_attn9_plan<<<(n_items + 7) / 8, 256>>>(d_work, n_items, nh, slopes, normtab, use_win, d_win, nullptr);
         CK(cudaDeviceSynchronize());
         std::vector<int4> win(n_items);
@@ -120,32 +147,50 @@ int main(int argc, char** argv) {
             printf("  v9 win=%d poly=%d lab=%2d %-34s %8.1f us  %7.1f TFLOP/s (algorithmic)  %6.0f cycles/block-half @1.9GHz\n", use_win, POLY, LAB, name, ms * 1e3, \
                    flops / (ms * 1e-3) / 1e12, ms * 1e-3 * 1.9e9 * sms / blocks);                                                 \
         }
+#define RUN10(POLY, LAB, name)                                                                                                    \
+        {                                                                                                                         \
+            const float ms = time_ms([&] { CK((launch_attn10_t<POLY, LAB>(tm, tmp, ctx, H, nh, slopes, d_work, d_win, lab_order, nwork, sms, 0, false))); }, 20); \
+            printf("  v10 win=%d poly=%d lab=%2d %-33s %8.1f us  %7.1f TFLOP/s (algorithmic)  %6.0f cycles/block-half @1.9GHz\n", use_win, POLY, LAB, name, ms * 1e3, \
+                   flops / (ms * 1e-3) / 1e12, ms * 1e-3 * 1.9e9 * sms / blocks);                                                 \
+        }
+        RUN10(3, 0, "baseline");
+        RUN10(0, 0, "all exp2 on MUFU");
+        RUN10(2, 0, "poly 1/2");
+        RUN10(4, 0, "poly 1/4");
+        if (use_win == 0) {
+            RUN10(3, 1, "no exponential");
+            RUN10(3, 2, "no row sum");
+            RUN10(3, 8, "no bf16 pack");
+            RUN10(3, 11, "no exp / sum / pack");
+        }
+        if (use_win) {
+            k_attn10_order<<<1, 1024>>>(d_win, n_items, 1, d_order);
+            CK(cudaDeviceSynchronize());
+            lab_order = d_order;
+            RUN10(3, 0, "baseline, cost-sorted snake order");
+            RUN10(4, 0, "poly 1/4, cost-sorted snake order");
+            const float ms = time_ms([&] { k_attn9_plan<<<(n_items + 7) / 8, 256>>>(d_work, n_items, nh, slopes, normtab, 1, d_win, nullptr); k_attn10_order<<<1, 1024>>>(d_win, n_items, 1, d_order); }, 50);
+            printf("  plan + order kernels: %.1f us per pair\n", ms * 1e3);
+        }
         RUN9(3, 0, "baseline");
         RUN9(0, 0, "all exp2 on MUFU");
         RUN9(2, 0, "poly 1/2");
         RUN9(4, 0, "poly 1/4");
         if (use_win == 0) {
             RUN9(3, 1, "no exponential");
-            RUN9(3, 2, "no row sum");
             RUN9(3, 4, "no offset add");
-            RUN9(3, 8, "no bf16 pack");
-            RUN9(3, 16, "no PV wait before P store");
-            RUN9(3, 3, "no exp, no row sum");
-            RUN9(3, 7, "no exp / sum / offset");
             RUN9(3, 15, "no exp / sum / offset / pack");
-            RUN9(0, 15, "same, poly 0");
-            RUN9(0, 1, "poly 0, no exponential");
         }
     }
     // ---- event trace of CTA 0 (LAB bit 5): per role (softmax half A / B quad 0, PV issuer, QK issuer) tagged clock64() stamps
-    for (int lab : {32, 32 + 15}) {
+    for (int lab : {32}) {
         long long* d_tr;
         CK(cudaMalloc(&d_tr, 4 * 1024 * sizeof(long long)));
         CK(cudaMemset(d_tr, 0, 4 * 1024 * sizeof(long long)));
         CK(cudaMemcpyToSymbol(g_a9_trace, &d_tr, sizeof(d_tr)));
         k_attn9_plan<<<(n_items + 7) / 8, 256>>>(d_work, n_items, nh, slopes, normtab, 0, d_win, nullptr);
         if (lab == 32) CK((launch_attn9_t<3, 32>(tm, ctx, H, nh, slopes, d_work, d_win, nwork, sms, 0, false)));
-        else CK((launch_attn9_t<3, 47>(tm, ctx, H, nh, slopes, d_work, d_win, nwork, sms, 0, false)));
+        else { }
         CK(cudaDeviceSynchronize());
         std::vector<long long> tr(4 * 1024);
         CK(cudaMemcpy(tr.data(), d_tr, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost));

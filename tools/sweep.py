@@ -47,6 +47,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     model = usdm_b200.Voicebox(**MODEL_CFG).eval()
+    for i, a in enumerate(sys.argv):                   # --opt name=value engine options (ablations), as bench.py
+        if a == "--opt" and i + 1 < len(sys.argv):
+            k, v = sys.argv[i + 1].split("=")
+            model.set_option(k, int(v))
     peaks = load_peaks()
     plen = torch.tensor([P])
 

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libtvb.so")
 SOURCES = ["tvb.cu"]
-HEADERS = ["common.cuh", "gemm_tc.cuh", "gemmln_tc.cuh", "attn_tc.cuh", "attn4_tc.cuh", "attn5_tc.cuh", "attn6_tc.cuh", "attn7_tc.cuh", "attn8_tc.cuh", "conv_tc.cuh", "glue.cuh", "simt.cuh", "vocoder.cuh", "vocoder_host.inl",
+HEADERS = ["common.cuh", "gemm_tc.cuh", "gemmln_tc.cuh", "attn_tc.cuh", "attn4_tc.cuh", "attn5_tc.cuh", "attn6_tc.cuh", "attn7_tc.cuh", "attn8_tc.cuh", "attn9_tc.cuh", "attn10_tc.cuh", "conv_tc.cuh", "glue.cuh", "simt.cuh", "vocoder.cuh", "vocoder_host.inl",
            os.path.join("..", "..", "include", "tvb.h"), os.path.join("..", "..", "include", "tvb_vocoder.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]

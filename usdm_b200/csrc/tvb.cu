@@ -23,6 +23,7 @@
 #include "attn7_tc.cuh"
 #include "attn8_tc.cuh"
 #include "attn9_tc.cuh"
+#include "attn10_tc.cuh"
 #include <algorithm>
 #include "conv_tc.cuh"
 #include "gemm_tc.cuh"
@@ -78,7 +79,7 @@ static int resolve_driver() {
 // 2-D row-major [rows, cols] (leading dimension ld elements), box = box_rows x box_cols (128 bytes wide), 128-byte swizzle.
 // Default element type bf16 (box 64 columns); f32 = true makes an fp32 map (box 32 columns).
 static int make_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols = 64,
-                     bool f32 = false, bool sw64 = false) {
+                     bool f32 = false, bool sw64 = false, bool sw32 = false) {
     TRY(resolve_driver());
     const int esz = f32 ? 4 : 2;
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
@@ -86,7 +87,7 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols
     cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw32 ? CU_TENSOR_MAP_SWIZZLE_32B : sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(TVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
                                        (long long)rows, (long long)cols, (long long)ld);
@@ -157,7 +158,13 @@ struct tvb_handle {
     int opt_gemm_mc = 0;        // CTA-pair GEMM: 1 = clusters of two pairs sharing the W tile by TMA multicast, 0 = independent pairs (default:
                                 // measured 7 % slower with multicast, profiles/r01: the pair kernel is not L2->SM bound after all)
     int opt_attn_ptmem = 1;     // tcgen05 attention v3: 1 = P kept in tensor memory (TS MMA), 0 = P staged through shared memory
-    int opt_attn_v = 9;         // tcgen05 attention kernel generation: 9 = attn9_tc.cuh (default), 8 .. 4 = attnN_tc.cuh, 3 = attn_tc.cuh
+    int opt_attn_v = 10;        // tcgen05 attention kernel generation: 10 = attn10_tc.cuh (default), 9 .. 4 = attnN_tc.cuh, 3 = attn_tc.cuh
+    int opt_attn_sort = 1;      // attention v10: items handed to the CTAs in descending planned cost, snake order (k_attn10_order): 0 = never (launch
+                                // order, stride), 2 = always, 1 = when the plan has long (>= 16 key blocks) or ragged sequences (default)
+    bool plan_sort = false;     // the rule of opt_attn_sort == 1 evaluated for the current plan
+    int* d_order = nullptr;
+    bf16* d_pos = nullptr;      // attention v10: [rows, 16] key-side operand of the bias MMA (key positions, k_attn10_pos), rebuilt with the plan
+    CUtensorMap tm_pos;
     int opt_attn_win = 1;       // attention v9: 1 = key blocks whose probabilities are provably below 2^-40 of the row sum are skipped (ALiBi
                                 // window, attn9_tc.cuh), 0 = every key block is processed (ablation / exactness check)
     float* normtab = nullptr;   // attention v9: [rows / 32][2 heads] row-block maxima of |q|^2, |k|^2, written by the QKV GEMM epilogue
@@ -644,8 +651,9 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     else if (!strcmp(name, "conv_halo")) h->opt_conv_halo = value ? 1 : 0;
     else if (!strcmp(name, "ln1_fold")) h->opt_ln1_fold = value ? 1 : 0;
     else if (!strcmp(name, "attn_ptmem")) h->opt_attn_ptmem = value ? 1 : 0;
-    else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 9) return fail(TVB_ERR_INVALID, "attn_v must be 3 .. 9"); h->opt_attn_v = value; }
+    else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 10) return fail(TVB_ERR_INVALID, "attn_v must be 3 .. 10"); h->opt_attn_v = value; }
     else if (!strcmp(name, "attn_win")) h->opt_attn_win = value ? 1 : 0;
+    else if (!strcmp(name, "attn_sort")) { if (value < 0 || value > 2) return fail(TVB_ERR_INVALID, "attn_sort must be 0, 1 or 2"); h->opt_attn_sort = value; }
     else if (!strcmp(name, "attn_poly")) { if (value != 0 && value != 2 && value != 3 && value != 4 && !(value >= 100 && value < 108)) return fail(TVB_ERR_INVALID, "attn_poly must be 0, 2, 3 or 4"); h->opt_attn_poly = value; }
     else if (!strcmp(name, "attn_pace")) h->opt_attn_pace = value ? 1 : 0;
     else if (!strcmp(name, "ln_fuse")) { if (value < 0 || value > 2) return fail(TVB_ERR_INVALID, "ln_fuse must be 0, 1 or 2"); h->opt_ln_fuse = value; }
@@ -752,6 +760,8 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
         TRY(dev_alloc_t(h, h->ws_owned, &h->d_tseq, sc));
         TRY(alloc_f32(h, &h->normtab, static_cast<size_t>(rows / 32 + 1) * 2 * c.num_attention_heads));
         TRY(dev_alloc_t(h, h->ws_owned, &h->d_win, static_cast<size_t>(w128c) * c.num_attention_heads));
+        TRY(dev_alloc_t(h, h->ws_owned, &h->d_pos, static_cast<size_t>(rows) * 16));
+        TRY(dev_alloc_t(h, h->ws_owned, &h->d_order, static_cast<size_t>(w128c) * c.num_attention_heads));
         TRY(alloc_f32(h, &h->base, static_cast<size_t>(rows) * H));
         TRY(alloc_f32(h, &h->xpre, static_cast<size_t>(rows) * H));
         TRY(alloc_f32(h, &h->xalt, static_cast<size_t>(rows) * H));
@@ -788,6 +798,8 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
     CK(cudaMemcpyAsync(h->d_seq, seqinfo.data(), sizeof(int) * seqinfo.size(), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_work16, work16.data(), sizeof(int2) * work16.size(), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_work128, work128.data(), sizeof(int4) * work128.size(), cudaMemcpyHostToDevice, st));
+    k_attn10_pos<<<(Mp + 255) / 256, 256, 0, st>>>(h->d_row_seq, h->d_row_pos, Mp, h->d_pos);
+    CKL();
     CK(cudaStreamSynchronize(st));   // host vectors go out of scope
     h->n_work16 = static_cast<int>(work16.size());
     h->n_work128 = static_cast<int>(work128.size());
@@ -799,6 +811,11 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
     h->L.seq_len = h->d_seq + nseq;
     h->L.seq_utt = h->d_seq + 2 * nseq;
     h->L.seq_uncond = h->d_seq + 3 * nseq;
+    {
+        int64_t lmin = lengths[0], lmax = lengths[0];
+        for (int b = 1; b < B; ++b) { lmin = std::min<int64_t>(lmin, lengths[b]); lmax = std::max<int64_t>(lmax, lengths[b]); }
+        h->plan_sort = static_cast<int>(work128.size()) * c.num_attention_heads >= 2 * h->num_sms && (lmax + 1 >= 16 * ATT_BK || lmin != lmax);
+    }
     h->plan_B = B; h->plan_T = T; h->plan_cfg = cfg_double; h->plan_half = half;
     h->plan_lengths.assign(lengths, lengths + B);
     h->plan_precision = h->precision;
@@ -815,6 +832,7 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
         TRY(make_tmap(&h->mid.tm_out, h->mid.b16, Mp, F, F, 32));
         TRY(make_tmap(&h->hbB.tm_out32, h->hbB.b16, Mp, H, H, 32, 32, false, true));
         TRY(make_tmap(&h->yop.tm, h->yop.b16, Mp, h->lin_y.K, h->lin_y.K, 128));
+        TRY(make_tmap(&h->tm_pos, h->d_pos, Mp, 16, 16, 128, 16, false, false, true));
         TRY(make_tmap(&h->tm_hin_halo, h->hin.b16, Mp, H, H, CH_ROWS));
         TRY(make_tmap(&h->tm_p1_halo, h->p1.b16, Mp, H, H, CH_ROWS));
         TRY(make_tmap(&h->hin.tm_out32, h->hin.b16, Mp, H, H, 32, 32, false, true));
@@ -1094,14 +1112,22 @@ static int attention(tvb_handle* h, cudaStream_t st) {
     const int H = h->cfg.hidden_size, nh = h->cfg.num_attention_heads;
     ProfScope ps(h, st, PC_ATTN);
     // bf16 path: q carries head_dim^-0.5 * log2(e) (tvb_finalize_weights), so tensor-core scores are already in the log2 domain
-    if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 9) {
+    if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && (h->opt_attn_v == 9 || h->opt_attn_v == 10)) {
         if (!h->norm_from_gemm) {         // QKV GEMM variant without the row-norm epilogue: take the norms from its output
             k_attn9_rownorm<<<(h->L.Mp + 31) / 32, 256, 0, st>>>(h->qkv.b16, h->L.Mp, H, nh, h->normtab);
             h->launches++;
             CKL();
         }
-        CK(launch_attn9_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->normtab, h->d_win, h->opt_attn_win,
-                            h->err_dev + 1, h->opt_attn_poly, h->num_sms, st, h->opt_pdl != 0));
+        if (h->opt_attn_v == 10)
+        {
+            const int sort = h->opt_attn_sort == 2 || (h->opt_attn_sort == 1 && h->plan_sort);
+            CK(launch_attn10_raw(h->qkv.tm, h->tm_pos, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->normtab, h->d_win, h->d_order,
+                                 h->opt_attn_win, sort, h->err_dev + 1, h->opt_attn_poly, h->num_sms, st, h->opt_pdl != 0));
+            if (sort && h->opt_attn_win) h->launches++;                // k_attn10_order
+        }
+        else
+            CK(launch_attn9_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->normtab, h->d_win, h->opt_attn_win,
+                                h->err_dev + 1, h->opt_attn_poly, h->num_sms, st, h->opt_pdl != 0));
         h->launches++;                    // k_attn9_plan
     } else if (h->precision == TVB_PRECISION_BF16 && h->opt_attn_tc && h->opt_attn_v == 8) {
         CK(launch_attn8_raw(h->qkv.tm, h->ctx.b16, H, nh, h->slopes, h->d_work128, h->n_work128, h->opt_attn_poly, h->num_sms, st, h->opt_attn_pace != 0, h->opt_pdl != 0));
@@ -1506,17 +1532,36 @@ extern "C" int tvb_debug_attention(int device, const void* qkv_dev, void* ctx_de
     int rc = make_tmap(&tm, qkv_dev, rows, 3 * H, 3 * H, 128);
     if (rc == TVB_OK) {
         cudaError_t e;
-        if (version == 9 || version == 90) {     // 90: every key block (no ALiBi window)
-            float* normtab = nullptr; int4* win = nullptr;
+        if (version == 9 || version == 90 || version == 10 || version == 100) {     // 90 / 100: every key block (no ALiBi window)
+            float* normtab = nullptr; int4* win = nullptr; bf16* pos = nullptr; int *rseq = nullptr, *rpos = nullptr, *order = nullptr;
             e = cudaMalloc(&normtab, static_cast<size_t>(rows / 32 + 1) * 2 * nheads * sizeof(float));
             if (e == cudaSuccess) e = cudaMalloc(&win, work.size() * nheads * sizeof(int4));
+            if (e == cudaSuccess) e = cudaMalloc(&pos, static_cast<size_t>(rows) * 16 * sizeof(bf16));
+            if (e == cudaSuccess) e = cudaMalloc(&rseq, static_cast<size_t>(rows) * sizeof(int));
+            if (e == cudaSuccess) e = cudaMalloc(&rpos, static_cast<size_t>(rows) * sizeof(int));
+            if (e == cudaSuccess) e = cudaMalloc(&order, work.size() * nheads * sizeof(int));
+            CUtensorMap tmp;
+            if (e == cudaSuccess) {
+                std::vector<int> hs(rows, -1), hp(rows, 0);
+                for (int s = 0; s < nseq; ++s)
+                    for (int i = 0; i < seq_len_host[s]; ++i) { hs[seq_start_host[s] + i] = s; hp[seq_start_host[s] + i] = i; }
+                cudaMemcpyAsync(rseq, hs.data(), sizeof(int) * rows, cudaMemcpyHostToDevice, st);
+                cudaMemcpyAsync(rpos, hp.data(), sizeof(int) * rows, cudaMemcpyHostToDevice, st);
+                k_attn10_pos<<<(rows + 255) / 256, 256, 0, st>>>(rseq, rpos, rows, pos);
+                cudaStreamSynchronize(st);
+                if (make_tmap(&tmp, pos, rows, 16, 16, 128, 16, false, false, true) != TVB_OK) e = cudaErrorInvalidValue;
+            }
             if (e == cudaSuccess) {
                 k_attn9_rownorm<<<(rows + 31) / 32, 256, 0, st>>>(static_cast<const bf16*>(qkv_dev), rows, H, nheads, normtab);
-                e = launch_attn9_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), normtab, win, version == 9, nullptr,
-                                     poly, prop.multiProcessorCount, st);
+                if (version >= 10 && version != 90)
+                    e = launch_attn10_raw(tm, tmp, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), normtab, win, order,
+                                          version == 10, 1, nullptr, poly, prop.multiProcessorCount, st);
+                else
+                    e = launch_attn9_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), normtab, win, version == 9, nullptr,
+                                         poly, prop.multiProcessorCount, st);
             }
             cudaStreamSynchronize(st);
-            cudaFree(normtab); cudaFree(win);
+            cudaFree(normtab); cudaFree(win); cudaFree(pos); cudaFree(rseq); cudaFree(rpos); cudaFree(order);
         }
         else if (version == 8) e = launch_attn8_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, prop.multiProcessorCount, st);
         else if (version == 7) e = launch_attn7_raw(tm, static_cast<bf16*>(ctx_dev), H, nheads, slopes_dev, d_work, (int)work.size(), poly, st);
