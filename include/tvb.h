@@ -73,9 +73,12 @@ int tvb_get_precision(const tvb_handle* h);
  * 0 = the CUDA-core kernel of the same op; both are GPU kernels of this library, there is no CPU path),
  * "gemm_2cta" (1 = CTA-pair tcgen05 GEMM, default; 0 = single-CTA tcgen05 GEMM), "gemm_mc" (1 = two CTA pairs per cluster
  * sharing the W tile by TMA multicast; 0 = independent pairs, default), "gemm_bn" (1 = the CTA-pair GEMM switches to 128-column tiles when
- * the 256-column tiling would leave CTA pairs idle -- small batches, default; 0 = always 256-column tiles), "attn_v" (8 = attn8_tc.cuh, 7 = attn7_tc.cuh, 6 = attn6_tc.cuh, 5 = attn5_tc.cuh, 4 = attn4_tc.cuh,
- * 3 = attn_tc.cuh), "attn_poly" (attention v4: 0 = every exp2 on MUFU; 2/3/4 = one element pair in n on the FMA-pipe
- * polynomial), "ln_fuse" (2 = LayerNorm computed inside the residual GEMM epilogue by 8-CTA clusters; 1 = LayerNorm
+ * the 256-column tiling would leave CTA pairs idle -- small batches, default; 0 = always 256-column tiles), "attn_v" (10 = attn10_tc.cuh, default; 9 = attn9_tc.cuh, 8 = attn8_tc.cuh (running-maximum softmax, any logit range), 7 .. 4 = attnN_tc.cuh,
+ * 3 = attn_tc.cuh), "attn_win" (v9+: 1 = skip key blocks whose probabilities are provably below 2^-40 of the row sum, default; 0 = process every
+ * block), "attn_sort" (v10: cost-sorted item order, 0 never / 1 for long or ragged plans, default / 2 always), "qkv_norm" (1 = the QKV GEMM
+ * epilogue emits the row-block norms attention v9+ bounds its logits with, default; 0 = a separate kernel), "attn_poly" (attention v4+: 0 = every
+ * exp2 on MUFU; 2/3/4 = one element pair in n on the FMA-pipe polynomial, default 4), "resid_l2" (residual GEMM epilogues pull their next
+ * chunks into the L2: 0 off, default -- measured slower; 1 / 2), "ln_fuse" (2 = LayerNorm computed inside the residual GEMM epilogue by 8-CTA clusters; 1 = LayerNorm
  * kernel emits bf16 + row statistics and the residual GEMM epilogue re-normalises the fp32 stream; 0 = separate fp32 LayerNorm output), "ln1_fold" (with ln_fuse = 1: 1 = the LayerNorm between attention and FFN is folded into the FFN-in GEMM, default;
  * 0 = it runs as a kernel), "zigzag" (1 = producer / consumer kernels walk the rows in opposite directions for L2 reuse,
  * default), "graph" (1 = tvb_solve replays the estimator pass of small batches as a CUDA graph, default; 0 = direct launches),
@@ -165,7 +168,7 @@ int tvb_debug_pair_gemm_bn(int32_t num_sms, int32_t rows, int32_t N);
 
 /* Kernel-level test hook (tests/ only): the tcgen05 attention kernel alone on packed [rows, 3H] bf16 q|k|v rows (q pre-scaled
  * by head_dim^-0.5 * log2(e)); sequence s occupies rows [seq_start[s], seq_start[s] + seq_len[s]).  ctx_dev bf16 [rows, H].
- * version: 8 = attn8_tc.cuh (persistent + two issue warps), 7 = attn7_tc.cuh (two issue warps), 6 = attn6_tc.cuh (persistent), 5 = attn5_tc.cuh, 4 = attn4_tc.cuh, 3 = attn_tc.cuh (P in tensor memory), 2 = attn_tc.cuh (P through shared memory).  Synchronises. */
+ * version: 10 = attn10_tc.cuh (100: the same without the ALiBi window), 9 = attn9_tc.cuh (90: without the window), 8 = attn8_tc.cuh (persistent + two issue warps), 7 = attn7_tc.cuh (two issue warps), 6 = attn6_tc.cuh (persistent), 5 = attn5_tc.cuh, 4 = attn4_tc.cuh, 3 = attn_tc.cuh (P in tensor memory), 2 = attn_tc.cuh (P through shared memory).  Synchronises. */
 int tvb_debug_attention(int device, const void* qkv_dev, void* ctx_dev, const int32_t* seq_start_host, const int32_t* seq_len_host,
                         int32_t nseq, int32_t rows, int32_t H, int32_t nheads, const float* slopes_dev, int32_t version,
                         int32_t poly, void* stream);

@@ -545,10 +545,11 @@ inline cudaError_t launch_attn10_raw(const CUtensorMap& tmQKV, const CUtensorMap
                                     int nwork, const float* normtab, int4* win, int* order, int use_window, int sort, int* err_flag, int poly,
                                     int num_sms, cudaStream_t st, bool pdl = false) {
     const int n_items = nwork * nheads;
-    k_attn9_plan<<<(n_items + 7) / 8, 256, 0, st>>>(work, n_items, nheads, slopes, normtab, use_window, win, err_flag);
+    cudaError_t e = launch_attn9_plan(work, n_items, nheads, slopes, normtab, use_window, win, err_flag, st, pdl);
+    if (e != cudaSuccess) return e;
     if (!(sort && use_window)) order = nullptr;
     if (order != nullptr) k_attn10_order<<<1, 1024, 0, st>>>(win, n_items, 1, order);
-    cudaError_t e = cudaGetLastError();
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     switch (poly) {
         case 0: return launch_attn10_t<0>(tmQKV, tmPos, ctx, H, nheads, slopes, work, win, order, nwork, num_sms, st, pdl);

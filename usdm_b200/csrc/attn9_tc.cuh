@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(256) k_attn9_plan(const int4* __restrict__ wor
                                                      const float* __restrict__ normtab, int use_window, int4* __restrict__ win,
                                                      int* __restrict__ err_flag) {
     pdl_launch_dependents();                           // the attention kernel's set-up may overlap this kernel
+    pdl_wait();                                        // (launched with programmatic serialization itself: the QKV GEMM must have finished)
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (t >= n_items) return;
@@ -549,6 +550,17 @@ attn9_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restric
     }
 }
 
+inline cudaError_t launch_attn9_plan(const int4* work, int n_items, int nheads, const float* slopes, const float* normtab, int use_window, int4* win,
+                                     int* err_flag, cudaStream_t st, bool pdl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((n_items + 7) / 8); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k_attn9_plan, work, n_items, nheads, slopes, normtab, use_window, win, err_flag);
+}
+
 template <int POLY, int LAB = 0>
 inline cudaError_t launch_attn9_t(const CUtensorMap& tmQKV, __nv_bfloat16* ctx, int H, int nheads, const float* slopes, const int4* work,
                                   const int4* win, int nwork, int num_sms, cudaStream_t st, bool pdl) {
@@ -574,8 +586,7 @@ inline cudaError_t launch_attn9_raw(const CUtensorMap& tmQKV, __nv_bfloat16* ctx
                                     int nwork, const float* normtab, int4* win, int use_window, int* err_flag, int poly, int num_sms,
                                     cudaStream_t st, bool pdl = false) {
     const int n_items = nwork * nheads;
-    k_attn9_plan<<<(n_items + 7) / 8, 256, 0, st>>>(work, n_items, nheads, slopes, normtab, use_window, win, err_flag);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_attn9_plan(work, n_items, nheads, slopes, normtab, use_window, win, err_flag, st, pdl);
     if (e != cudaSuccess) return e;
     switch (poly) {
         case 0: return launch_attn9_t<0>(tmQKV, ctx, H, nheads, slopes, work, win, nwork, num_sms, st, pdl);

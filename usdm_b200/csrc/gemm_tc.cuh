@@ -475,13 +475,13 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                 const int nbuf = (buf + 1 == G2_EPI_BUFS) ? 0 : buf + 1;
                 int col, row;
                 chunk_coords(tile, c, col, row);
-                // The accumulator chunk is requested first: the staging-buffer bookkeeping below (one lane waiting for a TMA store to
-                // finish reading shared memory) then overlaps the TMEM load instead of preceding it.
-                uint32_t racc[kChunkCols / 32][32];
-#pragma unroll
-                for (int q = 0; q < kChunkCols / 32; ++q) tmem_ld_32x32(t_acc + c * kChunkCols + q * 32, racc[q]);
-                if (lane == 0) {
-                    if constexpr (kResid) {
+                float v[kChunkCols];
+                if constexpr (kResid) {
+                    // The accumulator chunk is requested first: the staging-buffer bookkeeping below (one lane waiting for a TMA store to
+                    // finish reading shared memory) then overlaps the TMEM load instead of preceding it.
+                    uint32_t racc[32];
+                    tmem_ld_32x32(t_acc + c * kChunkCols, racc);
+                    if (lane == 0) {
                         // The next chunk's residual tile is prefetched into staging buffer nbuf, which (two buffers) was last read by the
                         // TMA store of the PREVIOUS chunk - the most recent bulk group.  Every committed store must therefore have
                         // finished reading its source before the load is issued: wait_group.read 0 (a store reads its 4 + 2 KB within a
@@ -504,17 +504,24 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                                 tma_prefetch_l2_2d(&tm.resid, fcol, frow);
                             }
                         }
-                    } else {
-                        tma_store_wait_read<G2_EPI_BUFS - 1>();   // the store issued G2_EPI_BUFS chunks ago (same buffer) is done reading
                     }
-                }
-                __syncwarp();
-                float v[kChunkCols];
+                    __syncwarp();
+                    tmem_ld_wait_dep(racc);
 #pragma unroll
-                for (int q = 0; q < kChunkCols / 32; ++q) {
-                    tmem_ld_wait_dep(racc[q]);
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(racc[j]);
+                } else {
+                    // (measured, profiles/r02: requesting both 32-column halves before the staging wait, as the residual branch does,
+                    // cost the GELU epilogue of FFN-in 8 % and QKV 4 % -- these epilogues are issue bound, not latency bound)
+                    if (lane == 0) tma_store_wait_read<G2_EPI_BUFS - 1>();   // the store issued G2_EPI_BUFS chunks ago (same buffer) is done reading
+                    __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[q * 32 + j] = __uint_as_float(racc[q][j]);
+                    for (int q = 0; q < kChunkCols / 32; ++q) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(t_acc + c * kChunkCols + q * 32, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[q * 32 + j] = __uint_as_float(r[j]);
+                    }
                 }
                 if constexpr (EPI == EPI_FOLD_GELU) {
                     const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
@@ -582,9 +589,16 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                 } else if constexpr (kBf16Out) {
                     if constexpr (EPI == EPI_BF16) {
                         if (p.rownorm != nullptr && col < p.rownorm_cols) {      // one 64-column chunk = one head of q or k
-                            float ss = 0.f;
+                            uint64_t ss2 = 0;                                      // two partial sums, packed (FFMA2)
 #pragma unroll
-                            for (int j = 0; j < kChunkCols; ++j) ss = fmaf(v[j], v[j], ss);
+                            for (int j = 0; j < kChunkCols; j += 2) {
+                                uint64_t x2;
+                                asm("mov.b64 %0, {%1, %2};" : "=l"(x2) : "f"(v[j]), "f"(v[j + 1]));
+                                asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(ss2) : "l"(x2));
+                            }
+                            float sa, sb;
+                            asm("mov.b64 {%0, %1}, %2;" : "=f"(sa), "=f"(sb) : "l"(ss2));
+                            const float ss = sa + sb;
                             const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(ss));
                             if (lane == 0) p.rownorm[static_cast<size_t>(row >> 5) * p.rownorm_ld + (col >> 6)] = __uint_as_float(mx);
                         }

@@ -159,6 +159,7 @@ struct tvb_handle {
                                 // measured 7 % slower with multicast, profiles/r01: the pair kernel is not L2->SM bound after all)
     int opt_attn_ptmem = 1;     // tcgen05 attention v3: 1 = P kept in tensor memory (TS MMA), 0 = P staged through shared memory
     int opt_attn_v = 10;        // tcgen05 attention kernel generation: 10 = attn10_tc.cuh (default), 9 .. 4 = attnN_tc.cuh, 3 = attn_tc.cuh
+    int opt_qkv_norm = 1;       // attention v9+: 1 = the QKV GEMM epilogue emits the row-block norms of q and k (default), 0 = a separate kernel reads them back
     int opt_attn_sort = 1;      // attention v10: items handed to the CTAs in descending planned cost, snake order (k_attn10_order): 0 = never (launch
                                 // order, stride), 2 = always, 1 = when the plan has long (>= 16 key blocks) or ragged sequences (default)
     bool plan_sort = false;     // the rule of opt_attn_sort == 1 evaluated for the current plan
@@ -653,6 +654,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     else if (!strcmp(name, "attn_ptmem")) h->opt_attn_ptmem = value ? 1 : 0;
     else if (!strcmp(name, "attn_v")) { if (value < 3 || value > 10) return fail(TVB_ERR_INVALID, "attn_v must be 3 .. 10"); h->opt_attn_v = value; }
     else if (!strcmp(name, "attn_win")) h->opt_attn_win = value ? 1 : 0;
+    else if (!strcmp(name, "qkv_norm")) h->opt_qkv_norm = value ? 1 : 0;
     else if (!strcmp(name, "attn_sort")) { if (value < 0 || value > 2) return fail(TVB_ERR_INVALID, "attn_sort must be 0, 1 or 2"); h->opt_attn_sort = value; }
     else if (!strcmp(name, "attn_poly")) { if (value != 0 && value != 2 && value != 3 && value != 4 && !(value >= 100 && value < 108)) return fail(TVB_ERR_INVALID, "attn_poly must be 0, 2, 3 or 4"); h->opt_attn_poly = value; }
     else if (!strcmp(name, "attn_pace")) h->opt_attn_pace = value ? 1 : 0;
@@ -1043,7 +1045,7 @@ static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, Li
         p.reverse = (rev && h->opt_zigzag) ? 1 : 0;
         p.resid_l2 = h->opt_resid_l2;
         if (cat == PC_GEMM_QKV) {         // attention v9 bounds its logits with row-block norms of q and k: the CTA-pair epilogue emits them
-            h->norm_from_gemm = h->opt_gemm_2cta && !h->opt_gemm_mc && epi == LE_PLAIN && lin.N == 3 * h->cfg.hidden_size;
+            h->norm_from_gemm = h->opt_qkv_norm && h->opt_attn_v >= 9 && h->opt_gemm_2cta && !h->opt_gemm_mc && epi == LE_PLAIN && lin.N == 3 * h->cfg.hidden_size;
             if (h->norm_from_gemm) { p.rownorm = h->normtab; p.rownorm_cols = 2 * h->cfg.hidden_size; p.rownorm_ld = 2 * h->cfg.num_attention_heads; }
         }
         const int e = epi == LE_PLAIN ? EPI_BF16 : epi == LE_GELU ? EPI_GELU_BF16 : epi == LE_RESID ? (ln ? EPI_RESID_LN : EPI_RESID_F32)
