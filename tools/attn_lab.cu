@@ -12,7 +12,8 @@
 
 #define A9_LAB_TRACE
 #define A10_LAB_TRACE
-#include "../usdm_b200/csrc/attn10_tc.cuh"
+#define A11_LAB_TRACE
+#include "../usdm_b200/csrc/attn11_tc.cuh"
 
 using namespace tvb;
 
@@ -153,6 +154,46 @@ int main(int argc, char** argv) {
             printf("  v10 win=%d poly=%d lab=%2d %-33s %8.1f us  %7.1f TFLOP/s (algorithmic)  %6.0f cycles/block-half @1.9GHz\n", use_win, POLY, LAB, name, ms * 1e3, \
                    flops / (ms * 1e-3) / 1e12, ms * 1e-3 * 1.9e9 * sms / blocks);                                                 \
         }
+#define RUN11(POLY, LAB, name)                                                                                                    \
+        {                                                                                                                         \
+            const float ms = time_ms([&] { CK((launch_attn11_t<POLY, LAB>(tm, tmp, ctx, H, nh, slopes, d_work, d_win, lab_order, nwork, sms, 0, false))); }, 20); \
+            printf("  v11 win=%d poly=%d lab=%2d %-33s %8.1f us  %7.1f TFLOP/s (algorithmic)  %6.0f cycles/block-half @1.9GHz\n", use_win, POLY, LAB, name, ms * 1e3, \
+                   flops / (ms * 1e-3) / 1e12, ms * 1e-3 * 1.9e9 * sms / blocks);                                                 \
+        }
+#define RUN11U(POLY, LAB, name)                                                                                                   \
+        {                                                                                                                         \
+            const float ms = time_ms([&] { CK((launch_attn11_t<POLY, LAB, 0>(tm, tmp, ctx, H, nh, slopes, d_work, d_win, lab_order, nwork, sms, 0, false))); }, 20); \
+            printf("  v11u win=%d poly=%d lab=%2d %-32s %8.1f us  %7.1f TFLOP/s (algorithmic)  %6.0f cycles/block-half @1.9GHz\n", use_win, POLY, LAB, name, ms * 1e3, \
+                   flops / (ms * 1e-3) / 1e12, ms * 1e-3 * 1.9e9 * sms / blocks);                                                 \
+        }
+        RUN11U(3, 0, "unsplit QK: baseline");
+        RUN11U(4, 0, "unsplit QK: poly 1/4");
+        RUN11U(2, 0, "unsplit QK: poly 1/2");
+        if (use_win == 0) { RUN11U(3, 1, "unsplit QK: no exponential"); RUN11U(3, 11, "unsplit QK: no exp / sum / pack"); }
+        RUN11(3, 0, "baseline");
+        RUN11(0, 0, "all exp2 on MUFU");
+        RUN11(2, 0, "poly 1/2");
+        RUN11(4, 0, "poly 1/4");
+        if (use_win == 0) {
+            RUN11(3, 1, "no exponential");
+            RUN11(3, 2, "no row sum");
+            RUN11(3, 8, "no bf16 pack");
+            RUN11(3, 11, "no exp / sum / pack");
+            // v11 against v10, bit for bit (same plan, same order of additions)
+            __nv_bfloat16* ctx2;
+            CK(cudaMalloc(&ctx2, (size_t)rows * H * 2));
+            CK(cudaMemset(ctx, 0, (size_t)rows * H * 2)); CK(cudaMemset(ctx2, 0, (size_t)rows * H * 2));
+            CK((launch_attn10_t<3, 0>(tm, tmp, ctx, H, nh, slopes, d_work, d_win, lab_order, nwork, sms, 0, false)));
+            CK((launch_attn11_t<3, 0>(tm, tmp, ctx2, H, nh, slopes, d_work, d_win, lab_order, nwork, sms, 0, false)));
+            CK(cudaDeviceSynchronize());
+            std::vector<uint16_t> h1((size_t)rows * H), h2((size_t)rows * H);
+            CK(cudaMemcpy(h1.data(), ctx, h1.size() * 2, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(h2.data(), ctx2, h2.size() * 2, cudaMemcpyDeviceToHost));
+            size_t diff = 0, nz = 0;
+            for (size_t i = 0; i < h1.size(); ++i) { diff += h1[i] != h2[i]; nz += h1[i] != 0; }
+            printf("  v11 vs v10: %zu of %zu outputs differ (%zu non-zero)\n", diff, h1.size(), nz);
+            cudaFree(ctx2);
+        }
         RUN10(3, 0, "baseline");
         RUN10(0, 0, "all exp2 on MUFU");
         RUN10(2, 0, "poly 1/2");
@@ -187,9 +228,9 @@ int main(int argc, char** argv) {
         long long* d_tr;
         CK(cudaMalloc(&d_tr, 4 * 1024 * sizeof(long long)));
         CK(cudaMemset(d_tr, 0, 4 * 1024 * sizeof(long long)));
-        CK(cudaMemcpyToSymbol(g_a9_trace, &d_tr, sizeof(d_tr)));
+        CK(cudaMemcpyToSymbol(g_a11_trace, &d_tr, sizeof(d_tr)));
         k_attn9_plan<<<(n_items + 7) / 8, 256>>>(d_work, n_items, nh, slopes, normtab, 0, d_win, nullptr);
-        if (lab == 32) CK((launch_attn9_t<3, 32>(tm, ctx, H, nh, slopes, d_work, d_win, nwork, sms, 0, false)));
+        if (lab == 32) CK((launch_attn11_t<3, 32>(tm, tmp, ctx, H, nh, slopes, d_work, d_win, nullptr, nwork, sms, 0, false)));
         else { }
         CK(cudaDeviceSynchronize());
         std::vector<long long> tr(4 * 1024);
@@ -201,7 +242,7 @@ int main(int argc, char** argv) {
                 if (tr[r * 1024 + i]) ev.push_back({tr[r * 1024 + i] & 0xffffffffffffll, r, (int)(tr[r * 1024 + i] >> 48)});
         std::sort(ev.begin(), ev.end(), [](const Ev& a, const Ev& b) { return a.t < b.t; });
         printf("# trace lab=%d (CTA 0; roles: 0/1 softmax half A/B warp 0, 2 PV issuer, 3 QK issuer; softmax tags: 1 scores seen, 2-5 chunk 0-3 in registers "
-               "(5 = S released), 6 math done, 7 PV wait done, 8 P handed over; PV: 20+h p_ready seen, 22+h issued; QK: 30+h s_free seen, 32+h issued)\n", lab);
+               "(3 = piece 0 released, 5 = piece 1 released), 6 block done; PV: 20+2h+piece p_ready seen; QK: 30+2h+piece s_free seen)\n", lab);
         const long long t0 = ev.empty() ? 0 : ev[0].t;
         int shown = 0;
         for (const Ev& e : ev) {

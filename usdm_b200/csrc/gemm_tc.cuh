@@ -65,6 +65,8 @@ struct GemmParams {
                               // the L2 one tile ahead (cp.async.bulk.prefetch.tensor), 2 = the chunk after the next one (the staged TMA load itself runs
                               // one chunk ahead).  Measured (profiles/r02): 1 costs the attention-out GEMM 7 % and FFN-out 4 % -- the kernel is HBM
                               // bandwidth bound (452 MB per 77 GFLOP launch), not latency bound, and the early lines are evicted before they are used
+    int lab;                  // timing ablations of the CTA-pair *_ST residual epilogue (option gemm_lab; results are WRONG with any bit set): bit 0 = the
+                              // residual tile is not loaded, bit 1 = no fp32 store, bit 2 = no bf16 copy store
     int reverse;              // CTA-pair kernels: walk the 256-row blocks from the last to the first.  Consumers traverse opposite to
                               // the kernel that produced their input, so the rows they read first are the ones still in the 126 MB L2.
 };
@@ -425,12 +427,20 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
             }
         };
         if constexpr (kResid) {
-            if (lane == 0 && cluster_id < num_tiles) {
+            if (lane == 0 && cluster_id < num_tiles && !(kStats && (p.lab & 1))) {
                 int col, row;
                 chunk_coords(cluster_id, 0, col, row);
                 mbar_arrive_expect_tx(&rb[0], G2_EPI_TILE);
                 tma_load_2d(stg, &tm.resid, &rb[0], col, row);
                 if (p.resid_l2 == 1) prefetch_tile_resid(cluster_id);
+            }
+        }
+        [[maybe_unused]] float4 ppn[4];                            // FOLD: the next tile's row-statistics partials of this thread's row
+        if constexpr (EPI == EPI_FOLD_GELU) {
+            if (p.part_n == 8 && cluster_id < num_tiles) {
+                const float4* pq = reinterpret_cast<const float4*>(p.part + static_cast<size_t>(tile_m0(cluster_id) + static_cast<int>(cta) * 128 + quad * 32 + lane) * 8);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ppn[q] = pq[q];
             }
         }
         int it = 0;
@@ -447,10 +457,18 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                 const float4* pp = reinterpret_cast<const float4*>(p.part + static_cast<size_t>(frow) * p.part_n);
                 float t1 = 0.f, t2 = 0.f;
                 if (p.part_n == 8) {
+                    // the four entries were requested one tile ahead (ppn): behind a finished accumulator their latency was 5 % of this
+                    // epilogue's stall samples (profiles/r02)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float4 a = pp[q];                    // (e_2q, e_2q+1)
+                        const float4 a = ppn[q];                   // (e_2q, e_2q+1)
                         t1 += a.x + a.z; t2 += a.y + a.w;
+                    }
+                    const int ntile = tile + num_clusters;
+                    if (ntile < num_tiles) {
+                        const float4* pq = reinterpret_cast<const float4*>(p.part + static_cast<size_t>(tile_m0(ntile) + static_cast<int>(cta) * 128 + quad * 32 + lane) * 8);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) ppn[q] = pq[q];
                     }
                 } else {
 #pragma unroll
@@ -464,6 +482,8 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                 fa = rstd; fb = -rstd * mean;
                 if ((tile % tiles_n) == 0 && chalf == 0) p.stats_out[frow] = make_float2(mean, rstd);
             }
+            [[maybe_unused]] float2 st = make_float2(0.f, 1.f);      // RESID_LN: (mean, rstd) of this thread's residual row, once per tile
+            if constexpr (kResidLn) st = p.ln_stats[tile_m0(tile) + static_cast<int>(cta) * 128 + quad * 32 + lane];
             mbar_wait(&tfull_bar[as], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256 + chalf * kHalf;
@@ -476,11 +496,25 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                 int col, row;
                 chunk_coords(tile, c, col, row);
                 float v[kChunkCols];
+                [[maybe_unused]] float4 cb4[8], cg4[8], cl4[8];     // residual epilogues: bias, LayerNorm gamma / beta of the chunk's 32 columns
                 if constexpr (kResid) {
                     // The accumulator chunk is requested first: the staging-buffer bookkeeping below (one lane waiting for a TMA store to
                     // finish reading shared memory) then overlaps the TMEM load instead of preceding it.
                     uint32_t racc[32];
                     tmem_ld_32x32(t_acc + c * kChunkCols, racc);
+                    // per-column constants of the chunk, requested before the waits below (ncu source view, profiles/r02: issued next to
+                    // their uses, the gamma / beta / bias loads were 29 % of this epilogue's stall samples)
+                    if (p.bias != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) cb4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
+                    }
+                    if constexpr (kResidLn) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            cg4[j] = __ldg(reinterpret_cast<const float4*>(p.ln_g + col) + j);
+                            cl4[j] = __ldg(reinterpret_cast<const float4*>(p.ln_b + col) + j);
+                        }
+                    }
                     if (lane == 0) {
                         // The next chunk's residual tile is prefetched into staging buffer nbuf, which (two buffers) was last read by the
                         // TMA store of the PREVIOUS chunk - the most recent bulk group.  Every committed store must therefore have
@@ -489,7 +523,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                         tma_store_wait_read<G2_EPI_BUFS - 2>();
                         int nt = tile, nc = c + 1;
                         if (nc == kChunks) { nc = 0; nt = tile + num_clusters; }
-                        if (nt < num_tiles) {
+                        if (nt < num_tiles && !(kStats && (p.lab & 1))) {
                             int ncol, nrow;
                             chunk_coords(nt, nc, ncol, nrow);
                             mbar_arrive_expect_tx(&rb[nbuf], G2_EPI_TILE);
@@ -523,6 +557,8 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                         for (int j = 0; j < 32; ++j) v[q * 32 + j] = __uint_as_float(r[j]);
                     }
                 }
+                // (measured, profiles/r02: requesting the per-column constants behind the TMEM load in the non-residual epilogues cost
+                // FFN-in 1 %; the residual epilogues, whose stall samples were 29 % gamma / beta / bias loads, gain 7 % from it)
                 if constexpr (EPI == EPI_FOLD_GELU) {
                     const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
                     const float4* c4 = reinterpret_cast<const float4*>(p.fold_c + col);
@@ -536,7 +572,8 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                     const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
                     for (int j = 0; j < kChunkCols / 4; ++j) {
-                        const float4 b = __ldg(b4 + j);
+                        float4 b;
+                        if constexpr (kResid) b = cb4[j]; else b = __ldg(b4 + j);
                         v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
                     }
                 }
@@ -546,17 +583,14 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                 }
                 uint8_t* rowp = tile_s + lane * 128;               // this thread's row of the staging tile
                 if constexpr (kResid) {
-                    float2 st = make_float2(0.f, 1.f);
-                    if constexpr (kResidLn) st = p.ln_stats[row + lane];      // (mean, rstd) of this thread's residual row
-                    const float4* g4 = reinterpret_cast<const float4*>(p.ln_g + col);
-                    const float4* b4 = reinterpret_cast<const float4*>(p.ln_b + col);
+                    if (!(kStats && (p.lab & 1)))
                     mbar_wait(&rb[buf], bpar);                     // residual tile landed (async proxy -> visible after wait)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4* q4 = reinterpret_cast<float4*>(rowp + ((j ^ r7) << 4));
                         const float4 rr = *q4;
                         if constexpr (kResidLn) {
-                            const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
+                            const float4 g = cg4[j], b = cl4[j];
                             v[4 * j] += fmaf((rr.x - st.x) * st.y, g.x, b.x); v[4 * j + 1] += fmaf((rr.y - st.x) * st.y, g.y, b.y);
                             v[4 * j + 2] += fmaf((rr.z - st.x) * st.y, g.z, b.z); v[4 * j + 3] += fmaf((rr.w - st.x) * st.y, g.w, b.w);
                         } else {
@@ -624,8 +658,8 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_2d(&tm.out, tile_s, col, row);
-                    if constexpr (kStats) tma_store_2d(&tm.out2, stg2 + buf * G2_EPI_TILE2, col, row);
+                    if (!(kStats && (p.lab & 2))) tma_store_2d(&tm.out, tile_s, col, row);
+                    if constexpr (kStats) { if (!(p.lab & 4)) tma_store_2d(&tm.out2, stg2 + buf * G2_EPI_TILE2, col, row); }
                     tma_store_commit();
                 }
                 if (++buf == G2_EPI_BUFS) { buf = 0; bpar ^= 1; }

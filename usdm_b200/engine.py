@@ -78,7 +78,8 @@ _lib: Optional[C.CDLL] = None
 
 
 def library_path() -> str:
-    return _build.LIB
+    """The in-tree build; TVB_LIBRARY overrides it (A/B runs of two builds on one box, tools/runs/)."""
+    return os.environ.get("TVB_LIBRARY") or _build.LIB
 
 
 def load_library() -> C.CDLL:
