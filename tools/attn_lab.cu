@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #define A9_LAB_TRACE
@@ -50,6 +51,7 @@ static float time_ms(F&& fn, int iters) {
 }
 
 int main(int argc, char** argv) {
+    setvbuf(stdout, nullptr, _IOLBF, 0);
     const float scale = argc > 1 ? atof(argv[1]) : 0.45f;
     const int len = argc > 2 ? atoi(argv[2]) : 1134;
     const int nseq = argc > 3 ? atoi(argv[3]) : 32;

@@ -33,6 +33,12 @@ __global__ void __launch_bounds__(128, 1) k_mma(int n, long long* out) {
         for (int i = 0; i < n; ++i) {
             const int k = i & 3;
             if (MODE == 0) umma_ss(tb + (i & 1) * 128, da + 2 * k, db + 2 * k, idesc, 1);
+            else if (MODE == 3) umma_ss(tb, da + 2 * k, db + 2 * k, idesc, 1);
+            else if (MODE == 4) umma_ts(tb + 384 + (i & 1) * 64, tb + 256 + k * 8, dv + k * (2048 >> 4), make_idesc_bf16(128, 64, false, true), 1);
+            else if (MODE == 5) {
+                if (i & 1) umma_ts(tb + 384, tb + 256 + k * 8, dv + k * (2048 >> 4), make_idesc_bf16(128, 64, false, true), 1);
+                else umma_ss(tb, da + 2 * k, db + 2 * k, make_idesc_bf16(128, 128), 1);
+            }
             else if (MODE == 1) umma_ts(tb + 384, tb + 256 + k * 8, dv + k * (2048 >> 4), idesc, 1);
             else umma_ss(tb + (i & 1) * 128, da + 2 * k, dp, idesc, 1);
         }
@@ -44,6 +50,58 @@ __global__ void __launch_bounds__(128, 1) k_mma(int n, long long* out) {
     __syncthreads();
     tc_fence_after();
     if (threadIdx.x < 32) tmem_dealloc<512>(tb);
+}
+
+// tcgen05.ld throughput: every warp reads its lane quadrant, `n` loads of 32 (or 16) columns, DEPTH loads in flight between waits
+template <int COLS, int DEPTH>
+__global__ void __launch_bounds__(512, 1) k_ldtm(int n, long long* out, unsigned* sink) {
+    __shared__ uint32_t slot;
+    if (threadIdx.x < 32) tmem_alloc<512>(&slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = slot + ((static_cast<uint32_t>((threadIdx.x >> 5) & 3) * 32) << 16);
+    unsigned acc = 0;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int i = 0; i < n; i += DEPTH) {
+        if constexpr (COLS == 32) {
+            uint32_t r[DEPTH][32];
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) tmem_ld_32x32(tb + ((i + d) & 7) * 32, r[d]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) acc ^= r[d][0] ^ r[d][31];
+        } else {
+            uint32_t r[DEPTH][16];
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) tmem_ld_32x16(tb + ((i + d) & 15) * 16, r[d]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) acc ^= r[d][0] ^ r[d][15];
+        }
+    }
+    const long long t1 = clock64();
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+    if (acc == 0x12345678u) sink[0] = acc;
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc<512>(slot); }
+}
+template <int COLS, int DEPTH>
+static void run_ld(long long* d, unsigned* sink) {
+    const int n = 4096;
+    for (int warps : {1, 4, 8, 16}) {
+        k_ldtm<COLS, DEPTH><<<148, warps * 32>>>(n, d, sink);
+        k_ldtm<COLS, DEPTH><<<148, warps * 32>>>(n, d, sink);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long c = 0;
+        cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+        const double bytes = (double)n * warps * 32 * COLS * 4;
+        printf("tcgen05.ld 32x32b.x%-2d depth %d  warps %2d: %6.1f cycles per load per warp, %6.1f B/cycle/SM (%s)\n", COLS, DEPTH, warps, (double)c / n, bytes / c,
+               cudaGetErrorString(e));
+    }
 }
 
 template <int MODE, int N>
@@ -62,6 +120,10 @@ static void run(const char* name, long long* d) {
 int main() {
     long long* d;
     cudaMalloc(&d, 8);
+    run<3, 128>("SS, ONE accumulator (dependent chain)", d);
+    run<3, 64>("SS, ONE accumulator (dependent chain)", d);
+    run<4, 64>("TS, two accumulators alternating", d);
+    run<5, 128>("SS N=128 / TS N=64 interleaved (per MMA avg)", d);
     run<0, 256>("SS K-major sw128 A, B (QK^T)", d);
     run<0, 128>("SS K-major sw128 A, B (QK^T)", d);
     run<0, 64>("SS K-major sw128 A, B (QK^T)", d);
@@ -69,5 +131,11 @@ int main() {
     run<1, 64>("TS A in TMEM, B MN-major sw128 (PV)", d);
     run<2, 128>("SS sw128 A, sw32 B (bias step)", d);
     run<2, 64>("SS sw128 A, sw32 B (bias step)", d);
+    unsigned* sink;
+    cudaMalloc(&sink, 4);
+    run_ld<32, 1>(d, sink);
+    run_ld<32, 2>(d, sink);
+    run_ld<16, 2>(d, sink);
+    run_ld<16, 4>(d, sink);
     return 0;
 }

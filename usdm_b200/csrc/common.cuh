@@ -86,8 +86,27 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // try_wait with a suspend-time hint: a waiting thread is parked by the hardware until the phase completes (or the hint
 // expires) instead of re-issuing the poll every few cycles - fewer issue slots and less power spent by the many warps that
 // wait on barriers in these warp-specialised kernels (the chip runs at its power cap, so idle polling costs clock).
+// TVB_MBAR_SPIN (tools/attn_lab.cu builds only): 1 = try_wait without the hint, 2 = test_wait polling.  Measured on the attention kernels
+// (profiles/r02/attn_lab_wait*.txt): 225.8 / 230.5 us against 228.5 us with the hint -- the wake-up is not what the per-block chain waits for.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+#if defined(TVB_MBAR_SPIN) && TVB_MBAR_SPIN == 2
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+#elif defined(TVB_MBAR_SPIN)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
@@ -95,6 +114,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
+#endif
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
