@@ -254,6 +254,33 @@ int main(int argc, char** argv) {
         }
         cudaFree(d_tr);
     }
+    {   // fine trace of v10 (LAB bit 6): roles 0-3 softmax warps of half A, 4 QK issuer, 5 PV issuer
+        long long* d_tr;
+        CK(cudaMalloc(&d_tr, 8 * 1024 * sizeof(long long)));
+        CK(cudaMemset(d_tr, 0, 8 * 1024 * sizeof(long long)));
+        CK(cudaMemcpyToSymbol(g_a10_trace, &d_tr, sizeof(d_tr)));
+        k_attn9_plan<<<(n_items + 7) / 8, 256>>>(d_work, n_items, nh, slopes, normtab, 0, d_win, nullptr);
+        CK((launch_attn10_t<3, 64>(tm, tmp, ctx, H, nh, slopes, d_work, d_win, nullptr, nwork, sms, 0, false)));
+        CK(cudaDeviceSynchronize());
+        std::vector<long long> tr(8 * 1024);
+        CK(cudaMemcpy(tr.data(), d_tr, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        struct Ev { long long t; int role, tag; };
+        std::vector<Ev> ev;
+        for (int r = 0; r < 8; ++r)
+            for (int i = 0; i < 1024; ++i)
+                if (tr[r * 1024 + i]) ev.push_back({tr[r * 1024 + i] & 0xffffffffffffll, r, (int)(tr[r * 1024 + i] >> 48)});
+        std::sort(ev.begin(), ev.end(), [](const Ev& a, const Ev& b) { return a.t < b.t; });
+        printf("# fine trace v10 (CTA 0): fine 0-3 = softmax warps of half A (1 scores seen, 2 chunk 0 in regs, 5 S released, 8 P handed over), fine 4 = QK issuer "
+               "(30+h s_free seen, 40+h before issue, 42+h issued + committed, 32+h after syncwarp), fine 5 = PV issuer (20+h p_ready seen, 50+h issued, 22+h end)\n");
+        const long long t0 = ev.empty() ? 0 : ev[0].t;
+        int shown = 0;
+        for (const Ev& e : ev) {
+            if (e.t - t0 < 40000) continue;
+            printf("  %8lld fine %d tag %2d\n", e.t - t0, e.role, e.tag);
+            if (++shown >= 260) break;
+        }
+        cudaFree(d_tr);
+    }
     {
         const float ms = time_ms([&] { CK(launch_attn8_raw(tm, ctx, H, nh, slopes, d_work, nwork, 3, sms, 0, false, false)); }, 20);
         printf("  v8 poly=3 %-45s %8.1f us  %7.1f TFLOP/s\n", "", ms * 1e3, flops / (ms * 1e-3) / 1e12);

@@ -123,8 +123,15 @@ __device__ long long* g_a10_trace;
         if ((LAB & 32) && blockIdx.x == 0 && lane == 0 && tr_n < 1024)                                                       \
             g_a10_trace[(role) * 1024 + tr_n++] = (static_cast<long long>(tag) << 48) | (clock64() & 0xffffffffffffll);       \
     } while (0)
+// finer trace (LAB bit 6): roles 0-3 = the four softmax warps of half A, 4 = QK issuer, 5 = PV issuer; g_a10_trace holds 8 x 1024 stamps
+#define A10_STAMP2(role, tag)                                                                                                 \
+    do {                                                                                                                     \
+        if ((LAB & 64) && blockIdx.x == 0 && lane == 0 && tr_n < 1024)                                                       \
+            g_a10_trace[(role) * 1024 + tr_n++] = (static_cast<long long>(tag) << 48) | (clock64() & 0xffffffffffffll);       \
+    } while (0)
 #else
 #define A10_STAMP(role, tag) do { } while (0)
+#define A10_STAMP2(role, tag) do { } while (0)
 #endif
 
 // LAB (tools/attn_lab.cu only; the library always instantiates LAB = 0): timing ablations that switch pieces of the softmax body
@@ -271,6 +278,7 @@ attn10_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__
                     const int c = pvc[half]++;
                     mbar_wait(&p_ready[half], c & 1);
                     A10_STAMP(2, 20 + half);
+                    A10_STAMP2(5, 20 + half);
                     if (jj == 0) {                                                        // this PV overwrites O: the previous item's
                         if (cnt[half] > 0) mbar_wait(&o_free[half], (cnt[half] - 1) & 1); // epilogue must have read it out
                         ++cnt[half];
@@ -286,8 +294,10 @@ attn10_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__
                         umma_commit(&pv_done[2 * half + (c & 1)]);
                         if (half == last_half) umma_commit(&kv_empty[slot]);              // every MMA reading this stage has been issued
                     }
+                    A10_STAMP2(5, 50 + half);
                     __syncwarp();
                     A10_STAMP(2, 22 + half);
+                    A10_STAMP2(5, 22 + half);
                 }
                 if (++slot == A10_KV_STAGES) slot = 0;
             }
@@ -322,6 +332,7 @@ attn10_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__
                     const int c = qkc[half]++;
                     mbar_wait(&s_free[half], (c & 1) ^ 1);  // block c - 1 of this half is in its threads' registers (fresh barrier: passes)
                     A10_STAMP(3, 30 + half);
+                    A10_STAMP2(4, 30 + half);
                     tc_fence_after();
                     const uint32_t d = tmem_base + half * 128;
                     const uint64_t da = dq0 + static_cast<uint64_t>((qb * 2 + half) * (ATT_TILE_BYTES >> 4));
@@ -329,6 +340,7 @@ attn10_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__
                     const uint64_t dpos = dp0 + static_cast<uint64_t>(slot * (A10_STAGE_BYTES >> 4));
                     const int jd = w.qb0 + half;
                     const bool last = (jj == nblk - 1) && (half == last_half);
+                    A10_STAMP2(4, 40 + half);
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < ATT_D / 16; ++k) umma_ss(d, da + 2 * k, db + 2 * k, idesc_qk, k != 0);
@@ -340,8 +352,10 @@ attn10_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__
                             umma_commit(&ext_empty[qb]);
                         }
                     }
+                    A10_STAMP2(4, 42 + half);
                     __syncwarp();
                     A10_STAMP(3, 32 + half);
+                    A10_STAMP2(4, 32 + half);
                 }
                 if (++slot == A10_KV_STAGES) { slot = 0; kvpar ^= 1; }
             }
@@ -402,6 +416,7 @@ attn10_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__
                     const bool partial = GEN && (k0 + ATT_BK > len);
                     tmem_ld_wait_dep(ca);                    // chunk 0 (requested when the block's scores arrived)
                     if (quad == 0) A10_STAMP(half, 2);
+                    if (half == 0) A10_STAMP2(quad, 2);
                     tmem_ld_32x32(tmem_S + 32, cb);
                     uint64_t acc2 = pack2f(0.f, 0.f), accp2 = pack2f(0.f, 0.f);
                     auto proc = [&](uint32_t(&cur)[32], const int c) {
@@ -458,6 +473,7 @@ attn10_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__
                     proc(ca, 2);
                     tmem_ld_wait_dep(cb);
                     if (quad == 0) A10_STAMP(half, 5);
+                    if (half == 0) A10_STAMP2(quad, 5);
                     // the whole block is in registers: hand S back, the next QK^T overlaps the last chunk and the P hand-over
                     tc_fence_before();
                     mbar_arrive(&s_free[half]);
@@ -479,10 +495,12 @@ attn10_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__
                 tc_fence_before();
                 mbar_arrive(&p_ready[half]);
                 if (quad == 0) A10_STAMP(half, 8);
+                if (half == 0) A10_STAMP2(quad, 8);
                 ++cblk;
                 if (more) {                                  // scores of the half's next block: wait, then request their first 32 columns
                     mbar_wait(&s_full[half], cblk & 1);
                     if (quad == 0) A10_STAMP(half, 1);
+                    if (half == 0) A10_STAMP2(quad, 1);
                     tc_fence_after();
                     tmem_ld_32x32(tmem_S, ca);
                     jnext = a9_block(w, jj2);
