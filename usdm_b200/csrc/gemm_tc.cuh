@@ -562,11 +562,13 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                 if constexpr (EPI == EPI_FOLD_GELU) {
                     const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
                     const float4* c4 = reinterpret_cast<const float4*>(p.fold_c + col);
+                    const uint64_t fa2 = f2_dup(fa), fb2 = f2_dup(fb);
 #pragma unroll
                     for (int j = 0; j < kChunkCols / 4; ++j) {
                         const float4 b = __ldg(b4 + j), cc = __ldg(c4 + j);
-                        v[4 * j + 0] = fmaf(fa, v[4 * j + 0], fmaf(fb, cc.x, b.x)); v[4 * j + 1] = fmaf(fa, v[4 * j + 1], fmaf(fb, cc.y, b.y));
-                        v[4 * j + 2] = fmaf(fa, v[4 * j + 2], fmaf(fb, cc.z, b.z)); v[4 * j + 3] = fmaf(fa, v[4 * j + 3], fmaf(fb, cc.w, b.w));
+                        // fa * v + (fb * cc + b), two columns per FFMA2 (the scalar roundings)
+                        f2_unpack(f2_fma(fa2, f2_pack(v[4 * j + 0], v[4 * j + 1]), f2_fma(fb2, f2_pack(cc.x, cc.y), f2_pack(b.x, b.y))), v[4 * j + 0], v[4 * j + 1]);
+                        f2_unpack(f2_fma(fa2, f2_pack(v[4 * j + 2], v[4 * j + 3]), f2_fma(fb2, f2_pack(cc.z, cc.w), f2_pack(b.z, b.w))), v[4 * j + 2], v[4 * j + 3]);
                     }
                 } else if (p.bias != nullptr) {
                     const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
@@ -579,7 +581,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                 }
                 if constexpr (EPI == EPI_GELU_BF16 || EPI == EPI_FOLD_GELU) {
 #pragma unroll
-                    for (int j = 0; j < kChunkCols; ++j) v[j] = gelu_erf_fast(v[j]);
+                    for (int j = 0; j < kChunkCols; j += 2) gelu_erf_fast2(v[j], v[j + 1]);
                 }
                 uint8_t* rowp = tile_s + lane * 128;               // this thread's row of the staging tile
                 if constexpr (kResid) {
