@@ -65,6 +65,10 @@ struct GemmParams {
                               // the L2 one tile ahead (cp.async.bulk.prefetch.tensor), 2 = the chunk after the next one (the staged TMA load itself runs
                               // one chunk ahead).  Measured (profiles/r02): 1 costs the attention-out GEMM 7 % and FFN-out 4 % -- the kernel is HBM
                               // bandwidth bound (452 MB per 77 GFLOP launch), not latency bound, and the early lines are evicted before they are used
+    int a_l2;                 // CTA-pair kernels (ablation, default 0): the TMA producer pulls the activation k-block a_l2 blocks ahead of the one it loads
+                              // into the L2 (the n-tiles of a row block, which run on neighbouring clusters at the same time, share the k-blocks
+                              // between them).  Measured (profiles/r02): a whole tile ahead costs every GEMM 3-7 % (74 MB of prefetched rows
+                              // displace the weights and the live rows in the 126 MB L2)
     int lab;                  // timing ablations of the CTA-pair *_ST residual epilogue (option gemm_lab; results are WRONG with any bit set): bit 0 = the
                               // residual tile is not loaded, bit 1 = no fp32 store, bit 2 = no bf16 copy store
     int reverse;              // CTA-pair kernels: walk the 256-row blocks from the last to the first.  Consumers traverse opposite to
@@ -351,6 +355,8 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 const int m0 = tile_m0(tile) + static_cast<int>(cta) * 128;
                 const int n0 = (tile % tiles_n) * BN + static_cast<int>(cta) * kHalf;
+                const int ntile = tile + num_clusters;                       // L2 prefetch target (a_l2): this CTA's A rows of its next tile
+                const int pf_m0 = ntile < num_tiles ? tile_m0(ntile) + static_cast<int>(cta) * 128 : -1;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * G2_STAGE_BYTES;
@@ -358,6 +364,16 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                     const int k0 = kb * GEMM_BK;
                     if (k0 < p.K1) tma_load_2d_2cta(sa, &tm.a, &full_bar[stage], k0, m0);
                     else           tma_load_2d_2cta(sa, &tm.a2, &full_bar[stage], k0 - p.K1, m0);
+                    if (p.a_l2 > 0) {
+                        // a_l2 k-blocks ahead of the load just issued (beyond the shared-memory ring), continuing into the next tile's rows
+                        int pk = kb + p.a_l2, pm = m0, pt = tile;
+                        if (pk >= num_kb) { pk -= num_kb; pm = pf_m0; pt = ntile; }
+                        if (pm >= 0 && (pk % tiles_n) == (pt % tiles_n)) {
+                            const int pk0 = pk * GEMM_BK;
+                            if (pk0 < p.K1) tma_prefetch_l2_2d(&tm.a, pk0, pm);
+                            else            tma_prefetch_l2_2d(&tm.a2, pk0 - p.K1, pm);
+                        }
+                    }
                     if constexpr (NP == 2) {
                         // 64 of my 128 W rows, delivered to me and to the CTA with my pair position in the other pair
                         tma_load_2d_2cta_mc(sa + G2_A_BYTES + pair_id * (G2_B_BYTES / 2), &tm.b, &full_bar[stage], k0, n0 + pair_id * 64,

@@ -153,6 +153,7 @@ struct tvb_handle {
                                 // (the pass is ~230 launches; at B = 1 the host cannot feed them fast enough), 0 = always launch directly
     int opt_zigzag = 1;         // bf16 path: row-block traversal alternates between producer and consumer kernels (L2 reuse)
     int opt_resid_l2 = 0;       // CTA-pair residual GEMM epilogues prefetch residual chunks into the L2 ahead of their staged load (GemmParams::resid_l2; ablation)
+    int opt_a_l2 = 0;           // CTA-pair GEMM producers prefetch activation k-blocks this far ahead into the L2 (GemmParams::a_l2; ablation)
     int opt_gemm_lab = 0;       // timing ablations of the *_ST residual epilogue (GemmParams::lab): any non-zero value gives WRONG results
     int opt_gemm_bn = 1;        // CTA-pair GEMM: 1 = 128-column tiles when the 256-column tiling needs more (waves x tile width) -- small batches; 0 = always 256
     int ln_part_n = 8;          // entries per row the last *_ST GEMM wrote into ln_part (8: 256-column tiles, 16: 128-column tiles)
@@ -646,6 +647,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     else if (!strcmp(name, "gemm_bn")) h->opt_gemm_bn = value ? 1 : 0;
     else if (!strcmp(name, "resid_l2")) { if (value < 0 || value > 2) return fail(TVB_ERR_INVALID, "resid_l2 must be 0, 1 or 2"); h->opt_resid_l2 = value; }
     else if (!strcmp(name, "gemm_lab")) h->opt_gemm_lab = value & 7;
+    else if (!strcmp(name, "a_l2")) { if (value < 0 || value > 64) return fail(TVB_ERR_INVALID, "a_l2 must be 0 .. 64"); h->opt_a_l2 = value; }
     else if (!strcmp(name, "zigzag")) h->opt_zigzag = value ? 1 : 0;
     else if (!strcmp(name, "graph")) h->opt_graph = value ? 1 : 0;
     else if (!strcmp(name, "pdl")) h->opt_pdl = value ? 1 : 0;
@@ -1047,6 +1049,7 @@ static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, Li
         p.reverse = (rev && h->opt_zigzag) ? 1 : 0;
         p.resid_l2 = h->opt_resid_l2;
         p.lab = h->opt_gemm_lab;
+        p.a_l2 = h->opt_a_l2;
         if (cat == PC_GEMM_QKV) {         // attention v9 bounds its logits with row-block norms of q and k: the CTA-pair epilogue emits them
             h->norm_from_gemm = h->opt_qkv_norm && h->opt_attn_v >= 9 && h->opt_gemm_2cta && !h->opt_gemm_mc && epi == LE_PLAIN && lin.N == 3 * h->cfg.hidden_size;
             if (h->norm_from_gemm) { p.rownorm = h->normtab; p.rownorm_cols = 2 * h->cfg.hidden_size; p.rownorm_ld = 2 * h->cfg.num_attention_heads; }
