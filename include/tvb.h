@@ -85,7 +85,9 @@ int tvb_get_precision(const tvb_handle* h);
  * "pdl" (1 = GEMM / attention / LayerNorm kernels use programmatic dependent launch, default), "attn_pace" (attention v8 MUFU
  * pacing ablation, default 0), "frame_tc" / "out_tc" (1 = the per-pass frame projection of the ODE state / the output
  * projection run as tcgen05 GEMMs, default; 0 = the CUDA-core kernels), "conv_halo" (1 = positional conv fetches each
- * activation tile once with its halo, default; 0 = one fetch per tap), and "profile" (see tvb_profile_read). */
+ * activation tile once with its halo, default; 0 = one fetch per tap), "a_l2" (pair GEMM producers prefetch activation k-blocks this far
+ * ahead into the L2; 0 = off, default -- measured slower), "gemm_lab" (TIMING ablations of the attention-out epilogue: bit 0 no residual
+ * load, bit 1 no fp32 store, bit 2 no bf16 copy; any non-zero value gives WRONG results, default 0), and "profile" (see tvb_profile_read). */
 int tvb_set_option(tvb_handle* h, const char* name, int32_t value);
 
 /* Replaces: Transformer.forward(x, y, cond, t, lengths) (networks.py:302-374) — the per-step velocity estimator.
