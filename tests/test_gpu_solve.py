@@ -209,6 +209,38 @@ def test_unit_ids_outside_the_table_are_reported_not_dereferenced():
 
 
 @pytest.mark.timeout(900)
+def test_large_logits_switch_the_model_to_the_running_maximum_kernel():
+    """The default attention kernel (v10) supports logits inside a weight-dependent bound and the library reports a violation
+    asynchronously.  The host mirror checks the FIRST call after a weight upload synchronously and, when the bound is exceeded,
+    switches the model to the running-maximum kernel (attn_v = 8) and repeats the call - so a checkpoint with large logits works
+    out of the box, and the result is the reference's."""
+    import usdm_b200
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sd = {k: v.clone() for k, v in weights(0, True).items()}
+    for name in ("q_proj", "k_proj"):
+        sd[f"estimator.layers.3.attention.{name}.weight"] *= 12.0
+        sd[f"estimator.layers.3.attention.{name}.bias"] *= 12.0
+    m = usdm_b200.Voicebox(**CFG)
+    m.load_state_dict(sd)
+    m.eval()
+    x, cond, L = _inputs(21, 2, 160, [160, 97], 32)
+    y = torch.randn(2, 80, 160, generator=torch.Generator().manual_seed(3))
+    t = torch.tensor([0.6, 0.6])
+    with pytest.warns(RuntimeWarning, match="running-maximum"):
+        v = m.estimator(x.cuda(), y.cuda(), cond.cuda(), t, L)
+    assert m._options["attn_v"] == 8
+    m.check_async()                                            # nothing pending: the repeated call was clean
+    sdc = {k: w.cuda() for k, w in sd.items()}
+    with torch.no_grad():
+        ref = O.estimator_forward(sdc, CFG, x.cuda(), y.cuda(), cond.cuda(), t.cuda(), L.cuda())
+    e = rel_l2(v, ref)
+    print("large-logit weights, v8 after the automatic switch: rel-L2 vs oracle", e)
+    assert e < 3e-2
+    v2 = m.estimator(x.cuda(), y.cuda(), cond.cuda(), t, L)   # later calls: no synchronisation, same kernel, same bits
+    assert torch.equal(v, v2)
+
+
+@pytest.mark.timeout(900)
 def test_second_device_in_the_same_process():
     """Kernel attributes (the > 48 KB dynamic shared-memory opt-in) are per device: a handle created on another GPU of the same
     process must set them up again.  Needs two devices (gpurun --gpus 2); skipped otherwise."""

@@ -10,6 +10,7 @@ the CUDA library through the C ABI of include/tvb.h.  There is no PyTorch or CPU
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 from typing import Optional
 
 import numpy as np
@@ -114,6 +115,7 @@ class Voicebox(nn.Module, PyTorchModelHubMixin):
         self._uploaded_version = -1
         self._precision = E.PRECISION_BF16
         self._options = {}
+        self._probed_version = -1      # weights version whose first call has been checked synchronously (see _guarded)
 
     # ---- reference BaseModule API (model/base.py:13-37)
     @property
@@ -191,6 +193,30 @@ class Voicebox(nn.Module, PyTorchModelHubMixin):
             self._uploaded_version = self._weights_version
         return lib, self._handle
 
+    def _guarded(self, dev, lib, h, call):
+        """Run `call` (one enqueueing ABI call).  The default attention kernel keeps no running maximum and therefore only supports
+        logits inside a bound that depends on the WEIGHTS (2 max|q| max|k| <= 200 in the log2 domain, attn9_tc.cuh); the library finds
+        out on the device and reports it asynchronously.  So that a checkpoint with larger logits works out of the box, the FIRST
+        call after every weight upload is checked synchronously: if the bound was exceeded the handle switches to the running-maximum
+        kernel (attn_v = 8) for good and the call is repeated.  Later calls keep the asynchronous check (ValueError at the next call)."""
+        E.check(call())
+        if (self._probed_version == self._weights_version or self._precision != E.PRECISION_BF16
+                or self._options.get("attn_v", 10) < 9 or not self._options.get("attn_tc", 1)):
+            return                      # already checked, or a path that handles any logits
+        torch.cuda.current_stream(dev).synchronize()
+        try:
+            E.check(lib.tvb_async_status(h))
+        except ValueError as e:
+            if "attention logits" not in str(e) or self._options.get("attn_v", 10) < 9:
+                raise
+            warnings.warn("usdm_b200: these weights produce attention logits beyond the range of the default attention kernel; "
+                          "switching this model to the running-maximum kernel (attn_v = 8)", RuntimeWarning)
+            self.set_option("attn_v", 8)
+            E.check(call())
+            torch.cuda.current_stream(dev).synchronize()
+            E.check(lib.tvb_async_status(h))
+        self._probed_version = self._weights_version
+
     @staticmethod
     def _prep(x, *floats):
         if not floats[0].is_cuda:
@@ -227,8 +253,8 @@ class Voicebox(nn.Module, PyTorchModelHubMixin):
             raise ValueError("t must have one entry per batch element")
         lh, lp = self._host_lengths(lengths, B)
         out = torch.empty_like(y)
-        E.check(lib.tvb_estimator_forward(h, _dev_ptr(x), _dev_ptr(y), _dev_ptr(cond),
-                                          th.numpy().ctypes.data_as(C.POINTER(C.c_float)), lp, B, T, _dev_ptr(out), self._stream(dev)))
+        self._guarded(dev, lib, h, lambda: lib.tvb_estimator_forward(h, _dev_ptr(x), _dev_ptr(y), _dev_ptr(cond),
+                                                                     th.numpy().ctypes.data_as(C.POINTER(C.c_float)), lp, B, T, _dev_ptr(out), self._stream(dev)))
         return out
 
     # ---- CFM.sample (voicebox.py:51-72) -----------------------------------------------------------------
@@ -240,8 +266,8 @@ class Voicebox(nn.Module, PyTorchModelHubMixin):
         lh, lp = self._host_lengths(cond_lengths, B)
         tv = float(torch.as_tensor(t).detach().to("cpu", torch.float32).reshape(-1)[0])
         out = torch.empty_like(z)
-        E.check(lib.tvb_sample_cfg(h, _dev_ptr(x), _dev_ptr(z), _dev_ptr(cond), lp, B, T, tv, float(gradient_scale),
-                                   int(bool(speech_prompt)), _dev_ptr(out), self._stream(dev)))
+        self._guarded(dev, lib, h, lambda: lib.tvb_sample_cfg(h, _dev_ptr(x), _dev_ptr(z), _dev_ptr(cond), lp, B, T, tv, float(gradient_scale),
+                                                              int(bool(speech_prompt)), _dev_ptr(out), self._stream(dev)))
         return out, 0
 
     # ---- CFM.solve_euler / solve_heun (voicebox.py:74-138) ----------------------------------------------
@@ -270,9 +296,9 @@ class Voicebox(nn.Module, PyTorchModelHubMixin):
                 noise = torch.stack([torch.randn_like(cond) for _ in range(n_evals)])
         out = torch.empty_like(z)
         vel = torch.empty((n_evals, B, M, T), device=dev, dtype=torch.float32) if return_velocities else None
-        E.check(lib.tvb_solve(h, solver_id, _dev_ptr(x), _dev_ptr(z), _dev_ptr(cond), lp, B, T, P, n_steps,
-                              ts.numpy().ctypes.data_as(C.POINTER(C.c_float)), float(gradient_scale), int(bool(speech_prompt)),
-                              _dev_ptr(noise) if P > 0 else None, _dev_ptr(out), _dev_ptr(vel), self._stream(dev)))
+        self._guarded(dev, lib, h, lambda: lib.tvb_solve(h, solver_id, _dev_ptr(x), _dev_ptr(z), _dev_ptr(cond), lp, B, T, P, n_steps,
+                                                         ts.numpy().ctypes.data_as(C.POINTER(C.c_float)), float(gradient_scale), int(bool(speech_prompt)),
+                                                         _dev_ptr(noise) if P > 0 else None, _dev_ptr(out), _dev_ptr(vel), self._stream(dev)))
         if noise is not None:
             noise.record_stream(torch.cuda.current_stream(dev))
         return (out, vel) if return_velocities else out
