@@ -123,7 +123,11 @@ int tvb_solve(tvb_handle* h, int32_t solver, const int64_t* x_dev, const float* 
  * table (networks.py:305); here the lookup is kept in range and a sticky per-handle flag is raised instead.  Because no compute
  * call synchronises the device, the flag is reported by the NEXT tvb_estimator_forward / tvb_sample_cfg / tvb_solve on the
  * handle, or by this function (call it after synchronising the stream to learn about the call just made):
- * TVB_ERR_INVALID once, then cleared; TVB_OK otherwise.  Never synchronises. */
+ * TVB_ERR_INVALID once, then cleared; TVB_OK otherwise.  Never synchronises.
+ * The same channel carries two weight-dependent conditions of the bf16 fast paths (one report each; tvb_last_error() names the option
+ * that selects the safe sibling): attention logits beyond the range of the default attention kernel ("attn_v" = 8), and rows whose
+ * mean exceeds 8 standard deviations in the LayerNorm folded into the FFN-in GEMM ("ln1_fold" = 0).  A caller should synchronise and
+ * call this once after its first call with new weights and switch the option if told to (usdm_b200/voicebox.py: Voicebox._guarded). */
 int tvb_async_status(tvb_handle* h);
 
 /* ---- decoder glue either side of the sampler; stateless, no handle ----

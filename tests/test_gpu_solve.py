@@ -241,6 +241,39 @@ def test_large_logits_switch_the_model_to_the_running_maximum_kernel():
 
 
 @pytest.mark.timeout(900)
+def test_large_row_offsets_switch_the_model_to_the_separate_layernorm():
+    """The LayerNorm folded into the FFN-in GEMM multiplies the bf16-rounded RAW rows and removes mean * colsum afterwards: a row whose
+    mean is many standard deviations loses precision there (the reference rounds after normalising).  The library flags such rows
+    (|mean| * rstd > 8); the host mirror's first-call check then switches the model to ln1_fold = 0 and repeats the call."""
+    import usdm_b200
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sd = {k: v.clone() for k, v in weights(0, True).items()}
+    sd["estimator.layers.2.final_layer_norm.bias"] += 40.0          # every hidden channel of layer 3's input shifted by 40
+    m = usdm_b200.Voicebox(**CFG)
+    m.load_state_dict(sd)
+    m.eval()
+    x, cond, L = _inputs(22, 2, 160, [160, 97], 32)
+    y = torch.randn(2, 80, 160, generator=torch.Generator().manual_seed(4))
+    t = torch.tensor([0.6, 0.6])
+    with pytest.warns(RuntimeWarning, match="ln1_fold = 0"):
+        v = m.estimator(x.cuda(), y.cuda(), cond.cuda(), t, L)
+    assert m._options["ln1_fold"] == 0      # (the offset also inflates |q|, |k|: the attention kernel may have been switched as well)
+    m.check_async()
+    sdc = {k: w.cuda() for k, w in sd.items()}
+    with torch.no_grad():
+        ref = O.estimator_forward(sdc, CFG, x.cuda(), y.cuda(), cond.cuda(), t.cuda(), L.cuda())
+    e = rel_l2(v, ref)
+    print("row-offset weights, ln1_fold = 0 after the automatic switch: rel-L2 vs oracle", e)
+    assert e < 2e-2
+    m.set_option("ln1_fold", 1)                                      # what the switch avoided
+    vf = m.estimator(x.cuda(), y.cuda(), cond.cuda(), t, L)
+    torch.cuda.synchronize()
+    print("  the same with the folded LayerNorm forced on: rel-L2 vs oracle", rel_l2(vf, ref))
+    with pytest.raises(ValueError, match="ln1_fold = 0"):
+        m.check_async()
+
+
+@pytest.mark.timeout(900)
 def test_second_device_in_the_same_process():
     """Kernel attributes (the > 48 KB dynamic shared-memory opt-in) are per device: a handle created on another GPU of the same
     process must set them up again.  Needs two devices (gpurun --gpus 2); skipped otherwise."""

@@ -22,6 +22,7 @@ constexpr int GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;                 // 32 KB
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;       // 48 KB
 constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int GEMM_THREADS = 192;
+constexpr float GEMM_FOLD_MEAN_LIMIT = 8.0f;
 
 enum GemmEpilogue : int {
     EPI_BF16 = 0,        // out_bf16 = acc + bias
@@ -58,6 +59,10 @@ struct GemmParams {
     int part_n;               // 8 or 16, see `part`
     const float* fold_c;      // [N] column sums of the folded weight                                              (EPI_FOLD_GELU)
     float2* stats_out;        // [M] (mean, rstd), written once per row by the n == 0 tiles                        (EPI_FOLD_GELU)
+    int* fold_flag;           // EPI_FOLD_GELU: mapped host word set to 1 when a row's |mean| * rstd exceeds GEMM_FOLD_MEAN_LIMIT.  The folded LayerNorm
+                              // multiplies the bf16-rounded RAW row and subtracts mean * colsum afterwards, so the operand rounding is amplified by
+                              // |mean| / std against the reference's round-after-normalise; rows like that (a large common offset across the hidden
+                              // dimension) do not occur with random or ordinary weights, and when they do the caller should run with ln1_fold = 0
     float* rownorm;           // EPI_BF16, CTA-pair kernels: when set, normtab[row / 32][col / 64] = max over the 32 rows of the squared norm of the 64
     int rownorm_cols;         //   output columns (fp32 values before the bf16 rounding), for columns < rownorm_cols: the |q|, |k| row-block maxima
     int rownorm_ld;           //   the attention kernel bounds its logits with (attn9_tc.cuh); row stride rownorm_ld
@@ -496,7 +501,10 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                 const float mean = t1 * (1.0f / 1024.0f);
                 const float rstd = rsqrtf(fmaxf(t2 * (1.0f / 1024.0f) - mean * mean, 0.f) + 1e-5f);
                 fa = rstd; fb = -rstd * mean;
-                if ((tile % tiles_n) == 0 && chalf == 0) p.stats_out[frow] = make_float2(mean, rstd);
+                if ((tile % tiles_n) == 0 && chalf == 0) {
+                    p.stats_out[frow] = make_float2(mean, rstd);
+                    if (p.fold_flag != nullptr && !(fabsf(fb) <= GEMM_FOLD_MEAN_LIMIT)) *p.fold_flag = 1;     // also catches NaN
+                }
             }
             [[maybe_unused]] float2 st = make_float2(0.f, 1.f);      // RESID_LN: (mean, rstd) of this thread's residual row, once per tile
             if constexpr (kResidLn) st = p.ln_stats[tile_m0(tile) + static_cast<int>(cta) * 128 + quad * 32 + lane];

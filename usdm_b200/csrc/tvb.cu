@@ -347,6 +347,12 @@ static int take_async_error(tvb_handle* h) {
                                      "(2 max|q| max|k| > %g in the log2 domain, or non-finite activations); its output is invalid -- "
                                      "set option attn_v = 8 for such weights", static_cast<double>(A9_LOGIT_LIMIT));
     }
+    if (f && f[2]) {
+        f[2] = 0;
+        return fail(TVB_ERR_INVALID, "a previous call met rows whose mean exceeds %g standard deviations in the LayerNorm that is folded into the "
+                                     "FFN-in GEMM (the raw-row operand loses precision there); its output is less accurate than the tolerance -- "
+                                     "set option ln1_fold = 0 for such weights", static_cast<double>(GEMM_FOLD_MEAN_LIMIT));
+    }
     return TVB_OK;
 }
 extern "C" int tvb_async_status(tvb_handle* h) {
@@ -1058,7 +1064,7 @@ static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, Li
                     : epi == LE_RESID_ST ? (ln ? EPI_RESID_LN_ST : EPI_RESID_F32_ST) : epi == LE_FOLD_GELU ? EPI_FOLD_GELU : epi == LE_F32 ? EPI_F32 : EPI_DUAL;
         const int bn = (h->opt_gemm_2cta && !h->opt_gemm_mc) ? pair_gemm_bn(h, Mp, lin.N) : 256;
         if (epi == LE_RESID_ST) { p.part = h->ln_part; p.part_n = h->ln_part_n = (bn == 128) ? 16 : 8; }
-        if (epi == LE_FOLD_GELU) { p.part = h->ln_part; p.part_n = h->ln_part_n; p.stats_out = h->statsB; p.fold_c = lin.fold_c; }
+        if (epi == LE_FOLD_GELU) { p.part = h->ln_part; p.part_n = h->ln_part_n; p.stats_out = h->statsB; p.fold_c = lin.fold_c; p.fold_flag = h->err_dev + 2; }
         if ((epi == LE_RESID_ST || epi == LE_FOLD_GELU) && !(h->opt_gemm_2cta && !h->opt_gemm_mc && lin.N % 256 == 0))
             return fail(TVB_ERR_STATE, "internal: folded LayerNorm needs the CTA-pair GEMM");
         if (epi == LE_RESID_ST && lin.N != 1024) return fail(TVB_ERR_STATE, "internal: partial row statistics are laid out for N == 1024");
