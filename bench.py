@@ -282,6 +282,7 @@ def main():
     passes = w["nfe"]
     roof = None
     roof_hbm = None
+    roof_attn = None
     kernels = None
     if not args.no_profile:
         model.set_option("profile", 1)
@@ -303,6 +304,18 @@ def main():
             ms = prof[k][0]
             if ms > 0:
                 kernels[k]["tflops"] = fl[k] * passes / (ms / 1e3) / 1e12
+        # the attention kernel against the same tensor peak (its algorithmic FLOPs: 4 d S^2 per head, skipped key blocks still count); it is
+        # bound by the softmax side (MUFU.EX2 at 16 / clk / SM and the per-block hand-over chain), not by the tensor pipe
+        at_ms, at_n = prof.get("attention", (0.0, 0))
+        if at_ms > 0 and at_n > 0:
+            # attention launches per pass (the planning kernels that share the category are counted in at_n): one per layer
+            at_launch = MODEL_CFG["num_hidden_layers"] * passes
+            at_tf = fl["attention"] * passes / (at_ms / 1e3) / 1e12
+            roof_attn = dict(bound="tensor", kernel="attn10_kernel (fused QK^T + ALiBi + key mask + softmax + PV on tcgen05, 24 launches per pass)",
+                             achieved=at_tf, peak=peaks["sustained"], unit="TFLOP/s", frac=at_tf / peaks["sustained"],
+                             flops_per_launch=fl["attention"] * passes / at_launch, avg_launch_ms=at_ms / at_launch,
+                             peak_source=peaks["source"] + " bf16_tflops_sustained",
+                             note="softmax-bound (MUFU / hand-over chain): ncu 30 % tensor-pipe active, 46 % XU (profiles/r02/ncu_attn10_final_summary.txt)")
         # the row kernel of the path against the HBM roofline: LayerNorm reads the fp32 rows and writes the bf16
         # operand copy (6 B per element of the VALID tokens; per-row statistics and the dirty lines of the producer not counted)
         ln_ms, ln_n = prof.get("layernorm", (0.0, 0))
@@ -353,7 +366,7 @@ def main():
                     data="synthetic", config=bench_config(args, w), clocks=clocks,
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(x_host.numel() * 8 + cond_host.numel() * 4),
                              d2h_bytes_per_step=int(out_host.numel() * 4), timing="wall clock, max over ranks"),
-                    gpu_launches=int(launches), roofline=roof, roofline_hbm=roof_hbm,
+                    gpu_launches=int(launches), roofline=roof, roofline_hbm=roof_hbm, roofline_attention=roof_attn,
                     roofline_step=dict(bound="tensor", achieved=step_tflops, peak=peaks["sustained"], unit="TFLOP/s per GPU",
                                        frac=step_tflops / peaks["sustained"],
                                        note="algorithmic FLOPs of the whole solve (valid tokens) / device time"),
