@@ -86,7 +86,8 @@ int tvb_get_precision(const tvb_handle* h);
  * pacing ablation, default 0), "frame_tc" / "out_tc" (1 = the per-pass frame projection of the ODE state / the output
  * projection run as tcgen05 GEMMs, default; 0 = the CUDA-core kernels), "conv_halo" (1 = positional conv fetches each
  * activation tile once with its halo, default; 0 = one fetch per tap), "a_l2" (pair GEMM producers prefetch activation k-blocks this far
- * ahead into the L2; 0 = off, default -- measured slower), "gemm_lab" (TIMING ablations of the attention-out epilogue: bit 0 no residual
+ * ahead into the L2; 0 = off, default -- measured slower), "epi_direct" (fp32-output GEMM epilogues straight between registers and global memory instead of staged
+ * through shared memory: 0 = never, default; 1 = FFN-out only; 2 = all -- same bits, measured no faster), "gemm_lab" (TIMING ablations of the attention-out epilogue: bit 0 no residual
  * load, bit 1 no fp32 store, bit 2 no bf16 copy; any non-zero value gives WRONG results, default 0), and "profile" (see tvb_profile_read). */
 int tvb_set_option(tvb_handle* h, const char* name, int32_t value);
 

@@ -75,6 +75,22 @@ def test_gemm_epilogues(epi, pair):
 
 
 @pytest.mark.timeout(300)
+@pytest.mark.parametrize("pair", [0x100, 0x400])
+@pytest.mark.parametrize("epi", [2, 3, 4])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 1024, 1024), (1536, 1024, 2048)])
+def test_gemm_direct_fp32_epilogues(M, N, K, epi, pair):
+    """The unstaged epilogue (registers <-> global memory through tcgen05.ld.16x256b fragments, flag 0x800) gives the staged epilogue's
+    bits: residual add (2), fp32 + bf16 copy (3), plain fp32 (4), 256- and 128-column tiles."""
+    ref, resid, of_s, ob_s = _run(M, N, K, epi | pair, seed=epi + 21)
+    _, _, of_d, ob_d = _run(M, N, K, epi | pair | 0x800, seed=epi + 21)
+    assert torch.equal(of_s, of_d), f"fp32 outputs differ: max {(of_s - of_d).abs().max().item()}"
+    if epi == 3:
+        assert torch.equal(ob_s.float(), ob_d.float())
+    want = ref + resid if epi == 2 else ref
+    assert (of_d - want).abs().max().item() < 0.04
+
+
+@pytest.mark.timeout(300)
 @pytest.mark.parametrize("M,N,K", [(512, 256, 64), (512, 512, 128), (1024, 256, 512), (1024, 1024, 1024),
                                    (1536, 3072, 1024), (512, 1024, 4096), (148 * 128 * 2 + 512, 1024, 1024)])
 def test_gemm_cluster4_multicast_f32_epilogue(M, N, K):

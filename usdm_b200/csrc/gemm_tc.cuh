@@ -299,9 +299,19 @@ struct Gemm2Maps {
 // weight map): half-width tiles for launches whose 256-wide tiling leaves most CTA pairs idle (M <= a few 256-row blocks, i.e. the
 // single-utterance requests of the reference app: N = 1024 gives 4 tiles per row block, 24 pairs of 74 busy at B = 1) -- the
 // host picks the width that needs fewer (waves x tile time), see linear().
-template <int EPI, int NP, int BN = 256>
+// DIRECT (fp32-output epilogues, NP == 1; ablation, option epi_direct): the epilogue goes straight between registers and global memory
+// instead of through staging tiles.  The staged path moves every epilogue byte through shared memory twice (TMA in, LDS, STS, TMA out:
+// 640 KB per attention-out tile of 8192 MMA cycles) on top of what the operand ring and the MMA's own operand reads take from it.  Here
+// the accumulator is read with tcgen05.ld.16x256b (the MMA C-fragment layout: a quad of threads holds 8 consecutive columns of a row,
+// tools/tmem_layout.cu), so a warp's 8-byte accesses cover whole 32-byte sectors of 8 rows: sector-exact global loads of the residual
+// and stores of the result without any staging, and the same bits.  Measured: the K = 4096 GEMM's mainloop gains 1.5 % from the freed
+// shared-memory bandwidth, but wherever the epilogue is the critical path (K = 1024, attention-out: 82 -> 120 ms per solve) three 8-byte
+// accesses per two columns are LSU-issue bound -- so the staged path stays the default.
+template <int EPI, int NP, int BN = 256, int DIRECT = 0>
 __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmParams& p) {
     static_assert(BN == 256 || (BN == 128 && NP == 1), "tile width");
+    static_assert(!DIRECT || (NP == 1 && (EPI == EPI_RESID_F32 || EPI == EPI_RESID_LN || EPI == EPI_RESID_F32_ST || EPI == EPI_RESID_LN_ST ||
+                                          EPI == EPI_DUAL || EPI == EPI_F32)), "direct epilogue: fp32-output epilogues of the pair kernel");
     constexpr int kHalf = BN / 2;                     // accumulator columns (= W rows) owned by one CTA / one epilogue column half
     constexpr uint32_t kStageTx = G2_A_BYTES + kHalf * GEMM_BK * 2;   // bytes one CTA receives per k-block
     extern __shared__ uint8_t smem_raw[];
@@ -447,6 +457,123 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
                 }
             }
         };
+        if constexpr (DIRECT) {
+            constexpr bool kCopy = kStats || EPI == EPI_DUAL;          // bf16 copy of the result
+            const int lr = lane >> 2;                                  // row inside a 16-row group (and lr + 8)
+            const int lc = 2 * (lane & 3);                             // first of this thread's two columns inside an 8-column block
+            // residual of (tile, row group hh, chunk c): this thread's 2 rows x 4 column blocks x 2 columns
+            auto load_resid = [&](int tile, int hh, int c, float2 (&ra)[4], float2 (&rb)[4]) {
+                const int row = tile_m0(tile) + static_cast<int>(cta) * 128 + quad * 32 + hh * 16 + lr;
+                const int col = (tile % tiles_n) * BN + chalf * kHalf + c * 32 + lc;
+                const float* pa = p.resid + static_cast<size_t>(row) * p.ld_out + col;
+                const float* pb = pa + static_cast<size_t>(8) * p.ld_out;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    ra[b] = *reinterpret_cast<const float2*>(pa + 8 * b);
+                    rb[b] = *reinterpret_cast<const float2*>(pb + 8 * b);
+                }
+            };
+            [[maybe_unused]] float2 nra[4], nrb[4];                    // residual of the NEXT (row group, chunk), requested one step ahead
+            if constexpr (kResid) {
+                if (cluster_id < num_tiles) load_resid(cluster_id, 0, 0, nra, nrb);
+            }
+            int it = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+                const int as = it & 1;
+                const int row0 = tile_m0(tile) + static_cast<int>(cta) * 128 + quad * 32;
+                const int colw = (tile % tiles_n) * BN + chalf * kHalf;      // first of this warp's kHalf columns
+                [[maybe_unused]] float2 sta[2], stb[2];                       // RESID_LN: (mean, rstd) of this thread's 4 rows
+                if constexpr (kResidLn) {
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        sta[hh] = p.ln_stats[row0 + hh * 16 + lr];
+                        stb[hh] = p.ln_stats[row0 + hh * 16 + lr + 8];
+                    }
+                }
+                mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32 + hh * 16) << 16) + as * 256 + chalf * kHalf;
+                    const int rowa = row0 + hh * 16 + lr;
+                    float sa1 = 0.f, sa2 = 0.f, sb1 = 0.f, sb2 = 0.f;        // *_ST: this thread's part of the two rows' (sum, sum of squares) over the current 64-column group
+                    [[maybe_unused]] float ga1 = 0.f, ga2 = 0.f, gb1 = 0.f, gb2 = 0.f;   // ... and of the finished first group (256-column tiles)
+#pragma unroll 1
+                    for (int c = 0; c < kChunks; ++c) {
+                        uint32_t racc[16];
+                        tmem_ld_16x256b_x4(t_acc + c * 32, racc);
+                        const int col = colw + c * 32 + lc;
+                        // constants of this thread's 8 columns, and the next step's residual, requested before the waits
+                        float2 cb2[4], cg2[4], cl2[4];
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            cb2[b] = p.bias != nullptr ? __ldg(reinterpret_cast<const float2*>(p.bias + col + 8 * b)) : make_float2(0.f, 0.f);
+                            if constexpr (kResidLn) {
+                                cg2[b] = __ldg(reinterpret_cast<const float2*>(p.ln_g + col + 8 * b));
+                                cl2[b] = __ldg(reinterpret_cast<const float2*>(p.ln_b + col + 8 * b));
+                            }
+                        }
+                        float2 ra[4], rb[4];
+                        if constexpr (kResid) {
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) { ra[b] = nra[b]; rb[b] = nrb[b]; }
+                            int nt = tile, nh = hh, nc = c + 1;
+                            if (nc == kChunks) { nc = 0; if (++nh == 2) { nh = 0; nt = tile + num_clusters; } }
+                            if (nt < num_tiles) load_resid(nt, nh, nc, nra, nrb);
+                        }
+                        tmem_ld_wait_dep16(racc);
+                        float* oa = p.out_f32 + static_cast<size_t>(rowa) * p.ld_out + col;
+                        float* ob = oa + static_cast<size_t>(8) * p.ld_out;
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            float a0 = __uint_as_float(racc[4 * b + 0]) + cb2[b].x, a1 = __uint_as_float(racc[4 * b + 1]) + cb2[b].y;
+                            float b0 = __uint_as_float(racc[4 * b + 2]) + cb2[b].x, b1 = __uint_as_float(racc[4 * b + 3]) + cb2[b].y;
+                            if constexpr (kResidLn) {
+                                a0 += fmaf((ra[b].x - sta[hh].x) * sta[hh].y, cg2[b].x, cl2[b].x); a1 += fmaf((ra[b].y - sta[hh].x) * sta[hh].y, cg2[b].y, cl2[b].y);
+                                b0 += fmaf((rb[b].x - stb[hh].x) * stb[hh].y, cg2[b].x, cl2[b].x); b1 += fmaf((rb[b].y - stb[hh].x) * stb[hh].y, cg2[b].y, cl2[b].y);
+                            } else if constexpr (kResidPlain) {
+                                a0 += ra[b].x; a1 += ra[b].y; b0 += rb[b].x; b1 += rb[b].y;
+                            }
+                            *reinterpret_cast<float2*>(oa + 8 * b) = make_float2(a0, a1);
+                            *reinterpret_cast<float2*>(ob + 8 * b) = make_float2(b0, b1);
+                            if constexpr (kCopy) {
+                                __nv_bfloat16* ca = p.out_bf16 + static_cast<size_t>(rowa) * p.ld_out + col + 8 * b;
+                                *reinterpret_cast<uint32_t*>(ca) = pack_bf16x2(a0, a1);
+                                *reinterpret_cast<uint32_t*>(ca + static_cast<size_t>(8) * p.ld_out) = pack_bf16x2(b0, b1);
+                            }
+                            if constexpr (kStats) {
+                                sa1 += a0 + a1; sa2 = fmaf(a0, a0, fmaf(a1, a1, sa2));
+                                sb1 += b0 + b1; sb2 = fmaf(b0, b0, fmaf(b1, b1, sb2));
+                            }
+                        }
+                        if constexpr (kStats) {
+                            if (c & 1) {                               // a 64-column group is complete: reduce over the quad (fixed order), one lane writes
+#pragma unroll
+                                for (int o = 1; o <= 2; o <<= 1) {
+                                    sa1 += __shfl_xor_sync(0xffffffffu, sa1, o); sa2 += __shfl_xor_sync(0xffffffffu, sa2, o);
+                                    sb1 += __shfl_xor_sync(0xffffffffu, sb1, o); sb2 += __shfl_xor_sync(0xffffffffu, sb2, o);
+                                }
+                                const int gcol = colw + (c - 1) * 32;  // first column of the group
+                                if constexpr (BN == 256) {
+                                    if (c == 1) { ga1 = sa1; ga2 = sa2; gb1 = sb1; gb2 = sb2; }
+                                    else if ((lane & 3) == 0) {
+                                        p.part[static_cast<size_t>(rowa) * 8 + (gcol >> 7)] = make_float2(ga1 + sa1, ga2 + sa2);
+                                        p.part[static_cast<size_t>(rowa + 8) * 8 + (gcol >> 7)] = make_float2(gb1 + sb1, gb2 + sb2);
+                                    }
+                                } else if ((lane & 3) == 0) {
+                                    p.part[static_cast<size_t>(rowa) * 16 + (gcol >> 6)] = make_float2(sa1, sa2);
+                                    p.part[static_cast<size_t>(rowa + 8) * 16 + (gcol >> 6)] = make_float2(sb1, sb2);
+                                }
+                                sa1 = sa2 = sb1 = sb2 = 0.f;
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], static_cast<uint32_t>(2 * pair_id));
+            }
+        } else {
         if constexpr (kResid) {
             if (lane == 0 && cluster_id < num_tiles && !(kStats && (p.lab & 1))) {
                 int col, row;
@@ -695,6 +822,7 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
             if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], static_cast<uint32_t>(2 * pair_id));   // the pair leader's MMA thread owns accumulator reuse
         }
         if (lane == 0) tma_store_wait_read<0>();
+        }   // staged epilogue
     }
 
     tc_fence_before();
@@ -705,10 +833,10 @@ __device__ __forceinline__ void gemm_pair_body(const Gemm2Maps& tm, const GemmPa
     }
 }
 
-template <int EPI, int BN = 256>
+template <int EPI, int BN = 256, int DIRECT = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_tc_kernel(const __grid_constant__ Gemm2Maps tm, const GemmParams p) {
-    gemm_pair_body<EPI, 1, BN>(tm, p);
+    gemm_pair_body<EPI, 1, BN, DIRECT>(tm, p);
 }
 // Cluster of 4 = two CTA pairs sharing the W tile by TMA multicast; tm.b must be the box-64 weight map; M % 512 == 0.
 template <int EPI>

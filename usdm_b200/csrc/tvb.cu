@@ -154,6 +154,12 @@ struct tvb_handle {
     int opt_zigzag = 1;         // bf16 path: row-block traversal alternates between producer and consumer kernels (L2 reuse)
     int opt_resid_l2 = 0;       // CTA-pair residual GEMM epilogues prefetch residual chunks into the L2 ahead of their staged load (GemmParams::resid_l2; ablation)
     int opt_a_l2 = 0;           // CTA-pair GEMM producers prefetch activation k-blocks this far ahead into the L2 (GemmParams::a_l2; ablation)
+    int opt_epi_direct = 0;     // CTA-pair GEMM, fp32-output epilogues (ablation): registers <-> global memory directly (tcgen05.ld.16x256b fragments,
+                                // sector-exact 8-byte accesses; gemm_tc.cuh: DIRECT) instead of staged through shared-memory tiles and TMA.  0 = never
+                                // (default), 1 = the FFN-out GEMM only, 2 = every fp32-output epilogue.  Same bits as the staged path.  Measured
+                                // (profiles/r02/bench_epi_direct_*.json): FFN-out 185.0 -> 182.5 ms per solve (K = 4096 hides the epilogue and the mainloop
+                                // gets the shared-memory bandwidth the staging took) but nothing at the step level; attention-out 82 -> 120 ms (where the
+                                // epilogue is the critical path the 8-byte accesses are LSU-issue bound)
     int opt_gemm_lab = 0;       // timing ablations of the *_ST residual epilogue (GemmParams::lab): any non-zero value gives WRONG results
     int opt_gemm_bn = 1;        // CTA-pair GEMM: 1 = 128-column tiles when the 256-column tiling needs more (waves x tile width) -- small batches; 0 = always 256
     int ln_part_n = 8;          // entries per row the last *_ST GEMM wrote into ln_part (8: 256-column tiles, 16: 128-column tiles)
@@ -653,6 +659,7 @@ extern "C" int tvb_set_option(tvb_handle* h, const char* name, int32_t value) {
     else if (!strcmp(name, "gemm_bn")) h->opt_gemm_bn = value ? 1 : 0;
     else if (!strcmp(name, "resid_l2")) { if (value < 0 || value > 2) return fail(TVB_ERR_INVALID, "resid_l2 must be 0, 1 or 2"); h->opt_resid_l2 = value; }
     else if (!strcmp(name, "gemm_lab")) h->opt_gemm_lab = value & 7;
+    else if (!strcmp(name, "epi_direct")) { if (value < 0 || value > 2) return fail(TVB_ERR_INVALID, "epi_direct must be 0, 1 or 2"); h->opt_epi_direct = value; }
     else if (!strcmp(name, "a_l2")) { if (value < 0 || value > 64) return fail(TVB_ERR_INVALID, "a_l2 must be 0 .. 64"); h->opt_a_l2 = value; }
     else if (!strcmp(name, "zigzag")) h->opt_zigzag = value ? 1 : 0;
     else if (!strcmp(name, "graph")) h->opt_graph = value ? 1 : 0;
@@ -891,11 +898,11 @@ static int launch_gemm_tc(tvb_handle* h, int epi, const CUtensorMap& tmA, const 
     return fail(TVB_ERR_INVALID, "unknown epilogue %d", epi);
 }
 
-template <int EPI, int BN = 256>
+template <int EPI, int BN = 256, int DIRECT = 0>
 static int launch_gemm2_tc_t(tvb_handle* h, const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st, int num_sms, int cat = PC_GEMM) {
     static PerDeviceOnce attr;
     if (!attr.done()) {
-        CK(cudaFuncSetAttribute(gemm2_tc_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(gemm2_tc_kernel<EPI, BN, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
         attr.mark();
     }
     const int tiles = (p.M / 256) * (p.N / BN);
@@ -907,7 +914,7 @@ static int launch_gemm2_tc_t(tvb_handle* h, const Gemm2Maps& maps, const GemmPar
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = (h && h->opt_pdl) ? 1 : 0;
-    CK(cudaLaunchKernelEx(&cfg, gemm2_tc_kernel<EPI, BN>, maps, p));
+    CK(cudaLaunchKernelEx(&cfg, gemm2_tc_kernel<EPI, BN, DIRECT>, maps, p));
     if (h) h->launches++;
     return TVB_OK;
 }
@@ -956,21 +963,25 @@ static int launch_gemm4_tc(tvb_handle* h, int epi, const Gemm2Maps& maps, const 
 // CTA-pair GEMM; maps.b must be the box-128 weight map (bn == 256) or the box-64 one (bn == 128), maps.out / maps.resid the epilogue
 // maps of the destination.
 static int launch_gemm2_tc(tvb_handle* h, int epi, const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st, int num_sms, int cat = PC_GEMM,
-                           int bn = 256) {
+                           int bn = 256, int direct = 0) {
     if (p.M % 256 || p.N % bn || p.K % GEMM_BK || p.K1 % GEMM_BK) return fail(TVB_ERR_INVALID, "gemm shape %dx%dx%d not tileable by CTA pairs", p.M, p.N, p.K);
 #define TVB_G2_CASE(E) case E: return bn == 128 ? launch_gemm2_tc_t<E, 128>(h, maps, p, st, num_sms, cat) : launch_gemm2_tc_t<E, 256>(h, maps, p, st, num_sms, cat);
+    // fp32-output epilogues: direct (register <-> global) or staged through shared memory
+#define TVB_G2_CASE_D(E) case E: if (direct) return bn == 128 ? launch_gemm2_tc_t<E, 128, 1>(h, maps, p, st, num_sms, cat) : launch_gemm2_tc_t<E, 256, 1>(h, maps, p, st, num_sms, cat); \
+                                 return bn == 128 ? launch_gemm2_tc_t<E, 128>(h, maps, p, st, num_sms, cat) : launch_gemm2_tc_t<E, 256>(h, maps, p, st, num_sms, cat);
     switch (epi) {
         TVB_G2_CASE(EPI_BF16)
         TVB_G2_CASE(EPI_GELU_BF16)
-        TVB_G2_CASE(EPI_RESID_F32)
-        TVB_G2_CASE(EPI_DUAL)
-        TVB_G2_CASE(EPI_F32)
-        TVB_G2_CASE(EPI_RESID_LN)
-        TVB_G2_CASE(EPI_RESID_F32_ST)
-        TVB_G2_CASE(EPI_RESID_LN_ST)
+        TVB_G2_CASE_D(EPI_RESID_F32)
+        TVB_G2_CASE_D(EPI_DUAL)
+        TVB_G2_CASE_D(EPI_F32)
+        TVB_G2_CASE_D(EPI_RESID_LN)
+        TVB_G2_CASE_D(EPI_RESID_F32_ST)
+        TVB_G2_CASE_D(EPI_RESID_LN_ST)
         TVB_G2_CASE(EPI_FOLD_GELU)
     }
 #undef TVB_G2_CASE
+#undef TVB_G2_CASE_D
     return fail(TVB_ERR_INVALID, "unknown epilogue %d", epi);
 }
 
@@ -1080,7 +1091,8 @@ static int linear(tvb_handle* h, const Lin& lin, const Act& a, const Act* a2, Li
                 return launch_gemm4_tc(h, e, maps, p, st, cat);
             }
             if (bn == 128) maps.b = lin.tm3;
-            return launch_gemm2_tc(h, e, maps, p, st, h->num_sms, cat, bn);
+            const int direct = h->opt_epi_direct == 2 || (h->opt_epi_direct == 1 && cat == PC_GEMM_F2 && e == EPI_RESID_LN);
+            return launch_gemm2_tc(h, e, maps, p, st, h->num_sms, cat, bn, direct);
         }
         return launch_gemm_tc(h, e, a.tm, a2 ? a2->tm : a.tm, lin.tm, p, st, h->num_sms, cat);
     }
@@ -1513,7 +1525,8 @@ extern "C" int tvb_debug_gemm_bf16(int device, const void* a_dev, const void* w_
         else maps.resid = maps.out;
         if (e == EPI_DUAL) TRY(make_tmap(&maps.out2, out_bf16_dev, M, N, N, 32, 32, false, true));
         if (mc) return launch_gemm4_tc(nullptr, e, maps, p, static_cast<cudaStream_t>(stream));
-        return launch_gemm2_tc(nullptr, e, maps, p, static_cast<cudaStream_t>(stream), prop.multiProcessorCount, PC_GEMM, bn128 ? 128 : 256);
+        const int direct = (epilogue & 0x800) != 0 && (e == EPI_RESID_F32 || e == EPI_DUAL || e == EPI_F32);   // direct fp32 epilogue
+        return launch_gemm2_tc(nullptr, e, maps, p, static_cast<cudaStream_t>(stream), prop.multiProcessorCount, PC_GEMM, bn128 ? 128 : 256, direct);
     }
     return launch_gemm_tc(nullptr, epilogue, tmA, tmA, tmB, p, static_cast<cudaStream_t>(stream), prop.multiProcessorCount);
 }
