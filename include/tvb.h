@@ -93,7 +93,7 @@ int tvb_set_option(tvb_handle* h, const char* name, int32_t value);
 
 /* Replaces: Transformer.forward(x, y, cond, t, lengths) (networks.py:302-374) — the per-step velocity estimator.
  * x_dev int64 [B,T]; y_dev, cond_dev fp32 [B,n_feats,T]; t_host fp32 [B]; lengths_host int64 [B];
- * out_v_dev fp32 [B,n_feats,T]. */
+ * out_v_dev fp32 [B,n_feats,T].  T <= 32767 (every compute call; TVB_ERR_INVALID beyond). */
 int tvb_estimator_forward(tvb_handle* h, const int64_t* x_dev, const float* y_dev, const float* cond_dev,
                           const float* t_host, const int64_t* lengths_host, int32_t B, int32_t T,
                           float* out_v_dev, void* stream);

@@ -209,6 +209,20 @@ def test_unit_ids_outside_the_table_are_reported_not_dereferenced():
 
 
 @pytest.mark.timeout(900)
+def test_sequences_beyond_the_supported_length_are_refused():
+    """Key positions reach the attention kernel as two bf16 terms that are exact below 2^15: longer inputs are an error, not a wrong bias."""
+    m = model(0, True, "bf16")
+    T = 32768
+    x = torch.zeros(1, T, dtype=torch.int64, device="cuda")
+    y = torch.zeros(1, 80, T, device="cuda")
+    with pytest.raises(ValueError, match="not supported"):
+        m.estimator(x, y, y, torch.tensor([0.5]), torch.tensor([T]))
+    v = m.estimator(x[:, :40], y[:, :, :40].contiguous(), y[:, :, :40].contiguous(), torch.tensor([0.5]), torch.tensor([40]))   # the handle is still usable
+    torch.cuda.synchronize()
+    assert torch.isfinite(v).all()
+
+
+@pytest.mark.timeout(900)
 def test_large_logits_switch_the_model_to_the_running_maximum_kernel():
     """The default attention kernel (v10) supports logits inside a weight-dependent bound and the library reports a violation
     asynchronously.  The host mirror checks the FIRST call after a weight upload synchronously and, when the bound is exceeded,

@@ -719,6 +719,8 @@ static int build_plan(tvb_handle* h, int B, int T, const int64_t* lengths, int c
     const tvb_config& c = h->cfg;
     if (!h->finalized) return fail(TVB_ERR_STATE, "tvb_finalize_weights has not been called");
     if (B <= 0 || T <= 0) return fail(TVB_ERR_INVALID, "B and T must be positive");
+    // key positions reach the attention kernel as two bf16 terms, p = (p & ~127) + (p & 127) (attn10_tc.cuh: k_attn10_pos): exact below 2^15
+    if (T + 1 > 32768) return fail(TVB_ERR_INVALID, "T = %d: sequences longer than 32767 frames (6 min 20 s at hop 256 / 22.05 kHz) are not supported", T);
     const int H = c.hidden_size, F = c.intermediate_size, nf = c.n_feats, nl = c.num_hidden_layers;
     const int GAP = 16;
     std::vector<int> off(B);
